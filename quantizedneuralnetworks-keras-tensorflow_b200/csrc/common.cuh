@@ -1,0 +1,130 @@
+// Shared host/device helpers for libqnnb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/qnnb200.h"
+
+namespace qnnb {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+#define QNNB_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) { ::qnnb::set_error(__VA_ARGS__); return QNNB_EINVAL; } \
+  } while (0)
+
+#define QNNB_CUDA(call)                                             \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return ::qnnb::cuda_fail(e__, #call);   \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// TensorFlow SAME padding: out = ceil(in/stride); total = max((out-1)*stride + k - in, 0);
+// before = total/2 (so 32 -> 16 under stride 2 with k=3 pads 0 before, 1 after).
+static inline void same_pad(int size, int k, int stride, int* out, int* before) {
+  int o = (size + stride - 1) / stride;
+  int total = (o - 1) * stride + k - size;
+  if (total < 0) total = 0;
+  *out = o;
+  *before = total / 2;
+}
+
+// ------------------------------------------------------------------ fused epilogue
+// Device-side copy of qnnb_epilogue plus derived constants.
+struct Epi {
+  float acc_scale;
+  const float* bias;
+  const float* bn_inv;
+  const float* bn_shift;
+  int   res_kind;
+  const void* residual;
+  float res_scale;
+  float res_mul;
+  int   act;
+  float qm;          // 2^(abits-1)
+  float leaky_alpha;
+  int   pool;
+};
+
+static inline Epi make_epi(const qnnb_epilogue& e) {
+  Epi d;
+  d.acc_scale = e.acc_scale;
+  d.bias = e.bias;
+  d.bn_inv = e.bn_inv;
+  d.bn_shift = e.bn_shift;
+  d.res_kind = e.res_kind;
+  d.residual = e.residual;
+  d.res_scale = e.res_scale;
+  d.res_mul = e.res_mul;
+  d.act = e.act;
+  d.qm = (float)(1 << ((e.abits > 0 ? e.abits : 1) - 1));
+  d.leaky_alpha = e.leaky_alpha;
+  d.pool = e.pool;
+  return d;
+}
+
+int validate_epilogue(const qnnb_epilogue& e, bool allow_pool, bool allow_residual);
+
+#ifdef __CUDACC__
+// Per-channel constants of the affine part (steps 1-3 of the fixed order).
+struct ChanConst {
+  float scale, bias, inv, shift;
+  bool  has_bias, has_bn;
+};
+
+__device__ __forceinline__ ChanConst load_chan(const Epi& e, int ch, bool valid) {
+  ChanConst c;
+  c.scale = e.acc_scale;
+  c.has_bias = (e.bias != nullptr);
+  c.has_bn = (e.bn_inv != nullptr);
+  c.bias = (c.has_bias && valid) ? __ldg(e.bias + ch) : 0.f;
+  c.inv = (c.has_bn && valid) ? __ldg(e.bn_inv + ch) : 1.f;
+  c.shift = (c.has_bn && valid) ? __ldg(e.bn_shift + ch) : 0.f;
+  return c;
+}
+
+// y = ((float(acc) * s) + bias) * inv + shift, each step a separate RN op (no FMA contraction).
+__device__ __forceinline__ float affine(float accf, const ChanConst& c) {
+  float v = __fmul_rn(accf, c.scale);
+  if (c.has_bias) v = __fadd_rn(v, c.bias);
+  if (c.has_bn) { v = __fmul_rn(v, c.inv); v = __fadd_rn(v, c.shift); }
+  return v;
+}
+
+// the affine map is non-decreasing in acc unless the BN slope is negative
+__device__ __forceinline__ bool decreasing(const ChanConst& c) { return c.has_bn && c.inv < 0.f; }
+
+__device__ __forceinline__ float add_residual(float y, float shortcut, float res_mul) {
+  return __fmul_rn(__fadd_rn(shortcut, y), res_mul);
+}
+
+// quantized_tanh -> integer level (rintf = round-half-to-even like tf.round)
+__device__ __forceinline__ int act_quant(float z, float qm) {
+  float q = rintf(__fmul_rn(z, qm));
+  q = fminf(fmaxf(q, -qm), qm - 1.f);
+  return (int)q;
+}
+
+// binary_tanh(z) == +1  <=>  z > 2^-24   
+__device__ __forceinline__ bool act_sign(float z) { return z > 5.9604644775390625e-08f; }
+
+__device__ __forceinline__ float act_leaky(float z, float alpha) { return z > 0.f ? z : __fmul_rn(alpha, z); }
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------ kernel launchers (one per .cu)
+int launch_pack_weights(int mode, int nb, float H, const float* w, int kh, int kw, int cin, int cout,
+                        int wfmt, void* out, float* scratch, cudaStream_t st);
+int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
+bool conv_tc_supported(const qnnb_conv_desc& d, const char** why);
+int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
+int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st);
+
+}  // namespace qnnb

@@ -1,0 +1,127 @@
+// K2 -- classifier head: Dense + bias (+ BatchNormalization | softmax), one warp per image.
+//
+// Stands in for QuantizedDense.call (layers/quantized_layers.py:79-88), BinaryDense.call
+// (layers/binary_layers.py:78-85), TernaryDense.call (layers/ternary_layers.py:77-84) followed by
+// the BatchNormalization of models/vgg.py:42 or the softmax of models/resnet.py:137.  The
+// reference's AveragePooling2D(8)+Flatten (models/resnet.py:134-135) is folded in by the host:
+// the packed kernel is replicated over the 64 pooled pixels and acc_scale carries the 1/64.
+//
+// HBM-bound (reads fin bytes per image, writes 40): x is read once, coalesced, 128 B per warp
+// per step; the packed kernel (<= 40 KB) stays in L1/L2.
+#include "common.cuh"
+
+namespace qnnb {
+
+namespace {
+
+constexpr int UG = 16;    // units accumulated per pass
+constexpr int MAX_UNITS = 32;
+
+struct DenseP {
+  int n, fin, units, kwords, fin_pad;
+  const void* x;
+  const void* w;
+  float* y;
+  float* logits;
+  int softmax;
+  Epi epi;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+dense_kernel(const DenseP p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_grid = gridDim.x * 8;
+  for (int img = blockIdx.x * 8 + warp; img < p.n; img += warps_per_grid) {
+    float z = 0.f;                       // lane u < units ends up with unit u's pre-activation
+    for (int u0 = 0; u0 < p.units; u0 += UG) {
+      const int ug = min(UG, p.units - u0);
+      if constexpr (KIND == QNNB_KIND_F32) {
+        float acc[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) acc[u] = 0.f;
+        const float* xr = (const float*)p.x + (long long)img * p.fin;
+        for (int k = lane; k < p.fin; k += 32) {
+          const float xv = __ldg(xr + k);
+#pragma unroll
+          for (int u = 0; u < UG; ++u)
+            if (u < ug) acc[u] = fmaf(xv, (float)__ldg((const int8_t*)p.w + (long long)(u0 + u) * p.fin_pad + k), acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+          float v = acc[u];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (u < ug && lane == u0 + u) z = v;
+        }
+      } else {
+        int acc[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) acc[u] = 0;
+        const uint32_t* xr = (const uint32_t*)p.x + (long long)img * p.kwords;
+        for (int k = lane; k < p.kwords; k += 32) {
+          const uint32_t xv = __ldg(xr + k);
+#pragma unroll
+          for (int u = 0; u < UG; ++u) {
+            if (u < ug) {
+              const uint32_t wv = __ldg((const uint32_t*)p.w + (long long)(u0 + u) * p.kwords + k);
+              if constexpr (KIND == QNNB_KIND_B1) acc[u] += __popc(xv ^ wv);
+              else acc[u] = __dp4a((int)xv, (int)wv, acc[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+          int v = acc[u];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if constexpr (KIND == QNNB_KIND_B1) v = p.fin - 2 * v;
+          if (u < ug && lane == u0 + u) z = (float)v;      // cvt.rn
+        }
+      }
+    }
+    const bool active = lane < p.units;
+    ChanConst cc = load_chan(p.epi, lane, active);
+    z = affine(z, cc);
+    if (p.softmax) {
+      if (active && p.logits) p.logits[(long long)img * p.units + lane] = z;
+      float m = active ? z : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float ex = active ? expf(z - m) : 0.f;
+      float s = ex;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      z = ex / s;
+    }
+    if (active) p.y[(long long)img * p.units + lane] = z;
+  }
+}
+
+}  // namespace
+
+int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st) {
+  QNNB_CHECK_ARG(d.units >= 1 && d.units <= MAX_UNITS, "dense: units=%d outside 1..%d", d.units, MAX_UNITS);
+  DenseP p;
+  p.n = d.n; p.fin = d.fin; p.units = d.units;
+  p.fin_pad = (d.fin + 3) / 4 * 4;
+  if (d.in_kind == QNNB_KIND_B1) p.kwords = (d.fin + 31) / 32;
+  else p.kwords = p.fin_pad / 4;
+  QNNB_CHECK_ARG(d.in_kind != QNNB_KIND_I8 || (d.fin & 3) == 0, "dense: int8 input needs fin %% 4 == 0 (got %d)", d.fin);
+  p.x = x; p.w = w; p.y = y; p.logits = logits; p.softmax = d.softmax;
+  p.epi = make_epi(d.epi);
+  int blocks = ceil_div(d.n, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  switch (d.in_kind) {
+    case QNNB_KIND_I8: dense_kernel<QNNB_KIND_I8><<<blocks, 256, 0, st>>>(p); break;
+    case QNNB_KIND_B1: dense_kernel<QNNB_KIND_B1><<<blocks, 256, 0, st>>>(p); break;
+    case QNNB_KIND_F32: dense_kernel<QNNB_KIND_F32><<<blocks, 256, 0, st>>>(p); break;
+    default: set_error("dense: bad in_kind %d", d.in_kind); return QNNB_EINVAL;
+  }
+  QNNB_CUDA(cudaGetLastError());
+  return QNNB_OK;
+}
+
+}  // namespace qnnb

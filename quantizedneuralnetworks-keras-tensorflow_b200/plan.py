@@ -1,0 +1,296 @@
+"""Fused inference plan: lowers a model graph to a short list of libqnnb200 kernel launches.
+
+Each custom conv / dense layer absorbs the layers that follow it in the reference's builders --
+``BatchNormalization``, the residual ``add`` (+ ``Lambda(x*0.5)``), the activation quantiser and
+``MaxPooling2D`` (models/vgg.py:15-37, models/resnet.py:57-129) -- into its kernel's epilogue, so
+every layer makes exactly one HBM round trip and activations stay int8 / bit-packed between
+layers.  ``AveragePooling2D(8) -> Flatten -> Dense`` (models/resnet.py:134-140) becomes one dense
+kernel over the un-pooled map with the packed kernel replicated per pixel.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import engine as E
+from . import kernels as K
+from .layers._base import QConv2DBase, QDenseBase
+
+F32 = np.float32
+MAX_CHUNK = 8192
+
+
+class _Step:
+    def __init__(self, kind, out, **kw):
+        self.kind, self.out = kind, out
+        self.__dict__.update(kw)
+        self.dev = {}
+
+
+def _act_of(layer):
+    if isinstance(layer, (E.Activation, E.LeakyReLU)):
+        return layer.act_spec()
+    return None
+
+
+class Plan:
+    def __init__(self, model, impl=L.IMPL_AUTO):
+        self.model = model
+        self.impl = int(impl)
+        ins, outs = model._graph()
+        self.order = E.topo_order(outs)
+        self.index = {id(t): i for i, t in enumerate(self.order)}
+        self.input_idx = self.index[id(ins[0])]
+        self.output_idx = self.index[id(outs[0])]
+        self.steps = []
+        self.launches = 0
+        self._compile()
+
+    # ------------------------------------------------------------------ compile
+    def _consumers(self):
+        cons = {i: [] for i in range(len(self.order))}
+        for j, t in enumerate(self.order):
+            for s in t.inputs:
+                cons[self.index[id(s)]].append(j)
+        return cons
+
+    def _compile(self):
+        order, index = self.order, self.index
+        cons = self._consumers()
+        done = set()
+        self.alias = {}
+
+        def sole(i):
+            return cons[i][0] if len(cons[i]) == 1 else None
+
+        for i, t in enumerate(order):
+            if i in done:
+                continue
+            lay = t.layer
+            src = [index[id(s)] for s in t.inputs]
+            if isinstance(lay, E.InputLayer):
+                continue
+            if isinstance(lay, QConv2DBase):
+                g = dict(layer=lay, src=src[0], bn=None, res=None, res_mul=1.0, act=lay._act, pool=False)
+                state = 3 if lay._act is not None else 0
+                cur = i
+                while True:
+                    nx = sole(cur)
+                    if nx is None or nx in done:
+                        break
+                    nl = order[nx].layer
+                    if isinstance(nl, E.BatchNormalization) and state < 1:
+                        g["bn"], state = nl, 1
+                    elif isinstance(nl, E.Add) and state < 2:
+                        other = [index[id(s)] for s in order[nx].inputs if index[id(s)] != cur]
+                        # the shortcut must already be materialised when this kernel runs
+                        if len(other) != 1 or other[0] >= i:
+                            break
+                        g["res"], state = other[0], 2
+                    elif isinstance(nl, E.Lambda) and state == 2 and g["res_mul"] == 1.0:
+                        g["res_mul"] = float(nl.multiplier)
+                    elif _act_of(nl) is not None and state < 3 and _act_of(nl)[0] in ("quant", "binary", "leaky", "linear"):
+                        g["act"], state = _act_of(nl), 3
+                    elif isinstance(nl, E.MaxPooling2D) and state < 4 and g["res"] is None:
+                        g["pool"], state = True, 4
+                    else:
+                        break
+                    done.add(nx)
+                    cur = nx
+                self.steps.append(_Step("conv", cur, **g))
+            elif isinstance(lay, QDenseBase):
+                g = dict(layer=lay, src=src[0], bn=None, softmax=(lay._act is not None and lay._act[0] == "softmax"))
+                if lay._act is not None and not g["softmax"]:
+                    raise ValueError("plan: Dense activation %r cannot be fused" % (lay._act,))
+                cur = i
+                nx = sole(cur)
+                if nx is not None and isinstance(order[nx].layer, E.BatchNormalization) and not g["softmax"]:
+                    g["bn"] = order[nx].layer
+                    done.add(nx)
+                    cur = nx
+                self.steps.append(_Step("dense", cur, **g))
+            elif isinstance(lay, E.Flatten):
+                self.alias[i] = ("flatten", src[0])
+            elif isinstance(lay, E.AveragePooling2D):
+                self.alias[i] = ("avgpool", src[0], lay.pool_size)
+            elif isinstance(lay, E.ZeroPadding2D):
+                self.steps.append(_Step("layer", i, layer=lay, src=src))
+            elif isinstance(lay, (E.BatchNormalization, E.Activation, E.LeakyReLU, E.MaxPooling2D, E.Add, E.Lambda)):
+                # not adjacent to a conv/dense: run the stand-alone fp32 kernel
+                self.steps.append(_Step("layer", i, layer=lay, src=src))
+            else:
+                raise ValueError("plan: layer %s (%s) is not supported on the accelerated path" % (lay.name, type(lay).__name__))
+        # sanity: every kernel input is the model input or the output of an earlier step
+        ready = {self.input_idx}
+        for st in self.steps:
+            needs = [st.src] if not isinstance(st.src, list) else list(st.src)
+            if getattr(st, "res", None) is not None:
+                needs.append(st.res)
+            for nd in needs:
+                while nd in self.alias:
+                    nd = self.alias[nd][1]
+                if nd not in ready:
+                    raise ValueError("plan: step for %s reads tensor %d before it is produced" % (st.layer.name, nd))
+            ready.add(st.out)
+        # every avgpool alias must feed flatten -> dense
+        for i, a in self.alias.items():
+            if a[0] == "avgpool":
+                for c in cons[i]:
+                    if not (c in self.alias and self.alias[c][0] == "flatten"):
+                        raise ValueError("plan: AveragePooling2D is only supported as AveragePooling2D -> Flatten -> Dense")
+
+    # ------------------------------------------------------------------ run
+    def _bn_dev(self, step, bn, dev):
+        key = ("bn", str(dev))
+        if key not in step.dev:
+            inv, shift = bn.constants()
+            step.dev[key] = (torch.from_numpy(inv).to(dev), torch.from_numpy(shift).to(dev))
+        return step.dev[key]
+
+    def _run_conv(self, st, env):
+        lay = st.layer
+        x = env[st.src]
+        dev = x.data.device
+        if x.kind == "b1" and lay.WEIGHT_KIND != "binary":
+            x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
+        wfmt = L.WFMT_B1 if x.kind == "b1" else L.WFMT_I8
+        _, _, _, wscale = lay.weight_mode()
+        scale = K.acc_scale(x.scale if x.kind in ("u8", "i8") else 1.0, wscale)
+        inv = shift = None
+        if st.bn is not None:
+            inv, shift = self._bn_dev(st, st.bn, dev)
+        res = None
+        if st.res is not None:
+            res = env[st.res]
+            if res.kind not in ("i8", "f32"):
+                res = K.QTensor("f32", res.to_float(), 1.0, res.channels)
+        act, abits, alpha = L.ACT_NONE, 0, 0.3
+        if st.act is not None:
+            if st.act[0] == "quant":
+                act, abits = L.ACT_QUANT, int(st.act[1])
+            elif st.act[0] == "binary":
+                act = L.ACT_SIGN
+            elif st.act[0] == "leaky":
+                act, alpha = L.ACT_LEAKY, float(st.act[1])
+        epi = K.make_epilogue(scale, bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift, residual=res,
+                              res_mul=st.res_mul, act=act, abits=abits, leaky_alpha=alpha, pool=2 if st.pool else 0)
+        env[st.out] = K.conv2d(x, lay.packed_kernel(dev, wfmt), lay.kernel_size[0], lay.kernel_size[1], lay.filters,
+                               lay.strides[0], epi, impl=self.impl)
+        self.launches += 1
+
+    def _resolve_dense_input(self, idx, env):
+        """Walk back through Flatten / AveragePooling2D aliases -> (QTensor [N, F], pool area)."""
+        pool = 1
+        cur = idx
+        flat = False
+        while cur in self.alias:
+            a = self.alias[cur]
+            if a[0] == "flatten":
+                flat = True
+            else:
+                pool *= int(a[2][0]) * int(a[2][1])
+                spatial = self.order[a[1]].shape
+                if spatial[1] != a[2][0] or spatial[2] != a[2][1]:
+                    raise ValueError("plan: AveragePooling2D must reduce the whole map (global pooling) to be fused")
+            cur = a[1]
+        return env[cur], pool, flat
+
+    def _run_dense(self, st, env):
+        lay = st.layer
+        x, pool, _ = self._resolve_dense_input(st.src, env)
+        dev = x.data.device
+        if x.kind == "u8":
+            x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
+        if x.kind == "b1" and (lay.WEIGHT_KIND != "binary" or x.channels % 32 != 0):
+            x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
+        if x.kind == "i8" and x.channels % 4 != 0:
+            x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
+        wfmt = L.WFMT_B1 if x.kind == "b1" else L.WFMT_I8
+        n = int(x.data.shape[0])
+        ch = x.channels
+        flat_shape = x.shape[1:]
+        fin = int(np.prod(flat_shape))
+        # pack the (in, units) kernel; under global average pooling the kernel has `ch` rows and is
+        # replicated over the pooled pixels
+        rows = lay.kernel.shape[0]
+        if pool > 1:
+            if rows != ch or fin != pool * ch:
+                raise ValueError("plan: dense kernel %s does not match pooled features %d" % (lay.kernel.shape, ch))
+            key = "pool%d" % pool
+            ck = (str(dev), wfmt, key)
+            if ck not in st.dev:
+                base = lay.packed_kernel(dev, wfmt)                 # [units][1][1][K]
+                st.dev[ck] = base.reshape(lay.units, 1, -1).repeat(1, pool, 1).contiguous()
+            wp = st.dev[ck]
+        else:
+            if rows != fin:
+                raise ValueError("plan: dense kernel rows %d != features %d" % (rows, fin))
+            wp = lay.packed_kernel(dev, wfmt)
+        _, _, _, wscale = lay.weight_mode()
+        xs = (x.scale if x.kind == "i8" else 1.0) / float(pool)
+        scale = K.acc_scale(xs, wscale)
+        inv = shift = None
+        if st.bn is not None:
+            inv, shift = self._bn_dev(st, st.bn, dev)
+        epi = K.make_epilogue(scale, bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift)
+        xin = K.QTensor(x.kind, x.data.reshape(n, -1), x.scale, fin if x.kind != "b1" else fin)
+        out, logits = K.dense(xin, wp, lay.units, epi, softmax=st.softmax, want_logits=st.softmax)
+        env[st.out] = K.QTensor("f32", out, 1.0, lay.units)
+        if logits is not None:
+            env["logits"] = logits
+        self.launches += 1
+
+    def run(self, x) -> dict:
+        """One forward over a device batch.  Returns the environment (tensor index -> QTensor)."""
+        env = {self.input_idx: K.as_qtensor(x)}
+        for st in self.steps:
+            if st.kind == "conv":
+                self._run_conv(st, env)
+            elif st.kind == "dense":
+                self._run_dense(st, env)
+            else:
+                ins = [env[s] for s in st.src]
+                y = st.layer.call(ins if isinstance(st.layer, E.Add) else ins[0])
+                env[st.out] = y if isinstance(y, K.QTensor) else K.as_qtensor(y)
+                self.launches += 1
+        return env
+
+    def forward(self, x, return_logits=False):
+        env = self.run(x)
+        out = env[self.output_idx]
+        out = out.data if out.kind == "f32" else out.to_float()
+        if return_logits:
+            return out, env.get("logits", out)
+        return out
+
+    def predict(self, x, batch_size=None, return_logits=False):
+        as_numpy = isinstance(x, np.ndarray)
+        if as_numpy:
+            if not torch.cuda.is_available():
+                raise RuntimeError("predict needs a CUDA device: this package has no CPU path")
+            xt = torch.from_numpy(np.ascontiguousarray(x)).cuda(non_blocking=True)
+        else:
+            xt = x
+        if not xt.is_cuda:
+            raise RuntimeError("predict needs a CUDA tensor: this package has no CPU path")
+        n = int(xt.shape[0])
+        bs = int(batch_size) if batch_size else min(max(n, 1), MAX_CHUNK)
+        outs, logs = [], []
+        for s in range(0, n, bs):
+            r = self.forward(xt[s:s + bs].contiguous(), return_logits=return_logits)
+            if return_logits:
+                outs.append(r[0]); logs.append(r[1])
+            else:
+                outs.append(r)
+        if n == 0:
+            units = self.order[self.output_idx].shape[-1]
+            out = torch.empty((0, units), dtype=torch.float32, device=xt.device)
+            logit = out
+        else:
+            out = torch.cat(outs) if len(outs) > 1 else outs[0]
+            logit = (torch.cat(logs) if len(logs) > 1 else logs[0]) if return_logits else None
+        if as_numpy:
+            out = out.cpu().numpy()
+            logit = logit.cpu().numpy() if logit is not None else None
+        return (out, logit) if return_logits else out

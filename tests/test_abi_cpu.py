@@ -1,0 +1,106 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every symbol
+include/qnnb200.h declares; ctypes structs match the header; no compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import qnn_b200 as q
+from qnn_b200 import _lib as L
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "qnnb200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qnnb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_built_and_loads():
+    assert os.path.exists(L.LIB_PATH), "libqnnb200.so must be built in-tree (python -c 'import __graft_entry__ as g; g.build()')"
+    h = L.lib()
+    assert h.qnnb_version() == 100
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    h = C.CDLL(L.LIB_PATH)
+    for s in syms:
+        assert hasattr(h, s), "missing export %s" % s
+        assert s in L.PROTOTYPES, "header symbol %s has no ctypes prototype" % s
+    for s in L.PROTOTYPES:
+        assert s in syms, "ctypes prototype %s is not declared in the header" % s
+
+
+def test_struct_layout_matches_header_constants():
+    src = open(HEADER).read()
+    for name, val in [("QNNB_KIND_U8", L.KIND_U8), ("QNNB_KIND_I8", L.KIND_I8), ("QNNB_KIND_B1", L.KIND_B1),
+                      ("QNNB_KIND_F32", L.KIND_F32), ("QNNB_ACT_QUANT", L.ACT_QUANT), ("QNNB_ACT_SIGN", L.ACT_SIGN),
+                      ("QNNB_ACT_LEAKY", L.ACT_LEAKY), ("QNNB_W_TERNARY", L.W_TERNARY), ("QNNB_WFMT_B1", L.WFMT_B1),
+                      ("QNNB_IMPL_TCGEN05", L.IMPL_TCGEN05)]:
+        m = re.search(r"#define\s+%s\s+(-?\d+)" % name, src)
+        assert m and int(m.group(1)) == val, name
+    # field order of the epilogue struct
+    body = re.search(r"typedef struct qnnb_epilogue \{(.*?)\} qnnb_epilogue;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(\w+)\s*;", body)
+    assert fields == [f[0] for f in L.Epilogue._fields_]
+    # sizes / offsets as the C compiler sees them
+    import subprocess
+    import tempfile
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "qnnb200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(qnnb_epilogue), sizeof(qnnb_conv_desc), sizeof(qnnb_dense_desc),
+         offsetof(qnnb_conv_desc, epi), offsetof(qnnb_dense_desc, epi), offsetof(qnnb_epilogue, residual),
+         offsetof(qnnb_epilogue, pool));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), "-o", os.path.join(td, "t"), os.path.join(td, "t.c")])
+        got = [int(v) for v in subprocess.check_output([os.path.join(td, "t")]).split()]
+    want = [C.sizeof(L.Epilogue), C.sizeof(L.ConvDesc), C.sizeof(L.DenseDesc), L.ConvDesc.epi.offset,
+            L.DenseDesc.epi.offset, L.Epilogue.residual.offset, L.Epilogue.pool.offset]
+    assert got == want
+
+
+def test_argument_errors_surface_without_a_gpu():
+    h = L.lib()
+    assert h.qnnb_packed_weight_bytes(L.WFMT_I8, 3, 3, 3, 64) == 64 * 9 * 4
+    assert h.qnnb_packed_weight_bytes(L.WFMT_B1, 3, 3, 64, 128) == 128 * 9 * 2 * 4
+    d = L.ConvDesc()
+    d.n, d.h, d.w, d.cin, d.cout, d.kh, d.kw, d.stride = 1, 8, 8, 4, 4, 5, 5, 1
+    d.epi.acc_scale = 1.0
+    d.epi.res_kind = L.KIND_NONE
+    oh, ow = C.c_int32(), C.c_int32()
+    rc = h.qnnb_conv2d_out_shape(C.byref(d), C.byref(oh), C.byref(ow))
+    assert rc == L.EINVAL
+    assert b"kernel 5x5" in h.qnnb_last_error()
+    with pytest.raises(L.QnnbError):
+        L.check(rc)
+    d.kh = d.kw = 3
+    d.stride = 2
+    d.epi.pool = 2
+    d.epi.act = L.ACT_QUANT
+    d.epi.abits = 4
+    assert h.qnnb_conv2d_out_shape(C.byref(d), C.byref(oh), C.byref(ow)) == 0
+    assert (oh.value, ow.value) == (2, 2)
+
+
+def test_no_cpu_fallback():
+    import numpy as np
+    import torch
+    from helpers import make_cf
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = q.build_model(make_cf())
+    with pytest.raises(RuntimeError):
+        m.predict(np.zeros((1, 32, 32, 3), np.uint8))
+    with pytest.raises(ValueError):
+        L.ptr(torch.zeros(4))

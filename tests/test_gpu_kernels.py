@@ -1,0 +1,310 @@
+"""GPU parity of every kernel against the exact oracle (O1), through the C ABI.
+Bit-exact for integer/bit outputs and for fp32 outputs produced from integer accumulators;
+tolerance (stated per test) only where the ACCUMULATION itself is floating point."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import exact  # noqa: E402
+from helpers import oracle_layer, unpack_bits  # noqa: E402
+
+F32 = np.float32
+
+
+def _seed(obj):
+    import zlib
+    return zlib.crc32(repr(obj).encode())
+
+
+def _mods():
+    import qnn_b200 as q
+    from qnn_b200 import _lib as L, kernels as K
+    return q, L, K
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# --------------------------------------------------------------------------- K0 packers
+@pytest.mark.parametrize("shape", [(3, 3, 3, 64), (3, 3, 64, 128), (1, 1, 16, 32), (3, 3, 5, 7), (1, 1, 4096, 10), (1, 1, 70, 3)])
+@pytest.mark.parametrize("mode", ["q2", "q4", "q8", "bin", "binH", "ter"])
+def test_pack_weights_matches_oracle(shape, mode):
+    q, L, K = _mods()
+    rng = np.random.default_rng(_seed((shape, mode)))
+    w = rng.uniform(-1, 1, size=shape).astype(F32)
+    # adversarial values: exact half-way points, zero, the binary threshold, saturation
+    flat = w.reshape(-1)
+    specials = np.array([0.0, -0.0, 2.0 ** -24, np.nextafter(F32(2.0 ** -24), F32(1)), 0.5, -0.5, 0.25, -0.25, 0.125,
+                         0.0625, 0.1875, -0.1875, 1.0, -1.0, 0.99999, 0.9375, 0.96875, 3 / 256, 5 / 256, -3 / 256], F32)
+    flat[: min(len(specials), flat.size)] = specials[: flat.size]
+    H = 1.0
+    if mode.startswith("q"):
+        nb = int(mode[1])
+        lv = exact.quantize_levels(w, nb)
+        got = K.pack_weights(dev(w), L.W_QUANT, nb, 1.0, L.WFMT_I8)
+    elif mode.startswith("bin"):
+        H = 0.75 if mode == "binH" else 1.0
+        lv = exact.binarize_levels(w, H)
+        got = K.pack_weights(dev(w), L.W_BINARY, 1, H, L.WFMT_I8)
+        gotb = K.pack_weights(dev(w), L.W_BINARY, 1, H, L.WFMT_B1).cpu().numpy()
+        wantb = exact.pack_bits_lastdim(np.transpose(lv, (3, 0, 1, 2)))
+        assert np.array_equal(gotb.astype(np.uint32), wantb)
+    else:
+        lv = exact.ternarize_levels(w, 1.0)
+        got = K.pack_weights(dev(w), L.W_TERNARY, 2, 1.0, L.WFMT_I8)
+    got = got.cpu().numpy()
+    kh, kw, cin, cout = shape
+    want = np.zeros((cout, kh, kw, (cin + 3) // 4 * 4), np.int8)
+    want[..., :cin] = np.transpose(lv, (3, 0, 1, 2))
+    assert np.array_equal(got, want)
+
+
+def test_quantiser_ops_known_answers():
+    """Hand-derivable KATs: level tables, half-to-even, binary threshold, ternary asymmetry."""
+    q, L, K = _mods()
+    from qnn_b200.layers import quantized_ops as qo, binary_ops as bo, ternary_ops as to
+    x = dev(np.array([[-1.0, -0.75, -0.5, -0.26, -0.25, 0.0, 0.24, 0.25, 0.5, 0.75, 0.76, 1.0]], F32))
+    got = qo.quantize(x, nb=2).cpu().numpy()[0]
+    #  x*2: -2,-1.5,-1,-.52,-.5,0,.48,.5,1,1.5,1.52,2 -> rint half-even: -2,-2,-1,-1,-0,0,0,0,1,2,2,2 -> clip[-2,1] /2
+    assert np.array_equal(got, np.array([-1, -1, -.5, -.5, 0, 0, 0, 0, .5, .5, .5, .5], F32))
+    assert np.array_equal(qo.quantized_tanh(x, nb=2).cpu().numpy()[0], got)
+    t = F32(2.0 ** -24)
+    b = dev(np.array([[0.0, -0.0, t, np.nextafter(t, F32(1)), -1e-3, 1e-3, 1.0, -1.0]], F32))
+    assert np.array_equal(bo.binary_tanh(b).cpu().numpy()[0], np.array([-1, -1, -1, 1, -1, 1, 1, -1], F32))
+    assert np.array_equal(bo.binarize(b, H=1).cpu().numpy()[0], np.array([-1, -1, -1, 1, -1, 1, 1, -1], F32))
+    w = np.array([[1.0, -1.0, 0.7, -0.7, 0.1, -0.1, 0.0, 0.5]], F32)        # mean|w| = 0.5125, cutoff = 0.35875
+    got = to.ternarize(dev(w), H=1).cpu().numpy()[0]
+    assert np.array_equal(got, np.array([1, -1, 1, -1, 0, 0, 0, 1], F32))
+    w2 = np.array([[0.5, -0.5, 0.5, -0.5]], F32)                             # cutoff 0.35
+    assert np.array_equal(to.ternarize(dev(w2), H=1).cpu().numpy()[0], np.array([1, -1, 1, -1], F32))
+    r = dev(np.array([[0.5, 1.5, 2.5, -0.5, -1.5, 0.49999997, 1e9]], F32))
+    assert np.array_equal(qo.round_through(r).cpu().numpy()[0], np.array([0, 2, 2, -0., -2, 0, 1e9], F32))
+
+
+# --------------------------------------------------------------------------- fused conv
+def _rand_input(rng, kind, shape, abits=4):
+    if kind == "u8":
+        return rng.integers(0, 256, size=shape, dtype=np.uint8), 1.0 / 255.0
+    if kind == "i8":
+        m = 1 << (abits - 1)
+        return rng.integers(-m, m, size=shape).astype(np.int8), 1.0 / m
+    if kind == "b1":
+        return (rng.integers(0, 2, size=shape) * 2 - 1).astype(np.int8), 1.0
+    return rng.normal(0, 1, size=shape).astype(F32), 1.0
+
+
+def _to_qtensor(K, kind, x, scale, abits=4):
+    if kind == "b1":
+        words = exact.pack_bits_lastdim(x).astype(np.int32)
+        return K.QTensor("b1", dev(words), 1.0, int(x.shape[-1]))
+    return K.QTensor(kind, dev(x), scale, int(x.shape[-1]))
+
+
+CONV_CASES = [
+    # kind, n, h, w, cin, cout, k, stride, wkind, nb, act, pool, bn, bias, res
+    ("u8", 3, 32, 32, 3, 64, 3, 1, "quantized", 4, "quant", True, True, True, None),
+    ("u8", 2, 28, 28, 1, 64, 3, 1, "quantized", 2, "quant", True, True, True, None),
+    ("u8", 2, 32, 32, 3, 16, 3, 1, "quantized", 4, "quant", False, True, False, None),
+    ("u8", 2, 32, 32, 3, 64, 3, 1, "binary", 1, "binary", True, True, True, None),
+    ("u8", 2, 32, 32, 3, 16, 3, 1, "quantized", 4, "leaky", False, True, False, None),
+    ("i8", 3, 16, 16, 64, 128, 3, 1, "quantized", 4, "quant", True, True, True, None),
+    ("i8", 2, 14, 14, 64, 64, 3, 1, "quantized", 2, "quant", True, True, True, None),
+    ("i8", 2, 7, 7, 64, 64, 3, 1, "quantized", 2, "quant", True, True, True, None),
+    ("i8", 2, 8, 8, 128, 256, 3, 1, "quantized", 8, "quant", True, True, True, None),
+    ("i8", 2, 32, 32, 16, 16, 3, 1, "quantized", 4, "quant", False, True, False, "i8"),
+    ("i8", 2, 32, 32, 16, 32, 3, 2, "quantized", 4, "quant", False, True, False, None),
+    ("i8", 2, 32, 32, 16, 32, 1, 2, "quantized", 4, None, False, False, False, None),
+    ("i8", 2, 16, 16, 32, 32, 3, 1, "quantized", 4, "quant", False, True, True, "f32"),
+    ("i8", 2, 9, 11, 20, 7, 3, 1, "ternary", 2, "quant", False, True, True, None),
+    ("i8", 2, 10, 10, 24, 40, 3, 2, "binary", 1, "quant", True, True, True, None),
+    ("i8", 1, 8, 8, 64, 64, 3, 1, "quantized", 8, None, False, False, True, None),
+    ("b1", 3, 16, 16, 64, 128, 3, 1, "binary", 1, "binary", True, True, True, None),
+    ("b1", 2, 8, 8, 128, 256, 3, 1, "binary", 1, "binary", True, True, True, None),
+    ("b1", 2, 12, 10, 40, 70, 3, 1, "binary", 1, "binary", False, True, False, None),
+    ("b1", 2, 16, 16, 32, 32, 3, 2, "binary", 1, "quant", False, True, False, None),
+    ("b1", 2, 16, 16, 32, 64, 1, 2, "binary", 1, None, False, False, True, None),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[("%s_%dx%d_%d-%d_k%ds%d_%s%d_%s%s%s" % (c[0], c[2], c[3], c[4], c[5], c[6], c[7], c[8][:3], c[9], c[10], "_pool" if c[11] else "", ("_res" + c[14]) if c[14] else "")) for c in CONV_CASES])
+@pytest.mark.parametrize("impl", ["generic"])
+def test_conv2d_integer_paths_bit_exact(case, impl):
+    q, L, K = _mods()
+    kind, n, h, w, cin, cout, k, stride, wkind, nb, act, pool, use_bn, use_bias, res = case
+    rng = np.random.default_rng(_seed(case))
+    abits = 8 if nb == 8 else (2 if nb == 2 else 4)
+    x, xs = _rand_input(rng, kind, (n, h, w, cin), abits)
+    kernel = rng.uniform(-1, 1, size=(k, k, cin, cout)).astype(F32)
+    fan = k * k * cin
+    bias = rng.uniform(-0.3, 0.3, size=cout).astype(F32) if use_bias else None
+    bn = None
+    if use_bn:
+        var_scale = fan * (0.11 if kind != "b1" else 1.0)
+        bn = (rng.uniform(0.3, 0.9, cout).astype(F32) * rng.choice([1, 1, -1], cout).astype(F32),
+              rng.uniform(-0.2, 0.2, cout).astype(F32),
+              (rng.uniform(-0.2, 0.2, cout) * np.sqrt(var_scale)).astype(F32),
+              (rng.uniform(0.5, 1.5, cout) * var_scale).astype(F32))
+    oh, ow = -(-h // stride), -(-w // stride)
+    residual = res_q = None
+    if res == "i8":
+        rl = rng.integers(-8, 8, size=(n, oh, ow, cout)).astype(np.int8)
+        residual = rl.astype(F32) * F32(1 / 8)
+        res_q = K.QTensor("i8", dev(rl), 1 / 8, cout)
+    elif res == "f32":
+        residual = rng.normal(0, 0.5, size=(n, oh, ow, cout)).astype(F32)
+        res_q = K.QTensor("f32", dev(residual), 1.0, cout)
+    want, _ = oracle_layer(x, kind, xs, kernel, wkind, nb, 1.0, stride, bias=bias, bn=bn, eps=1e-4, residual=residual,
+                           res_mul=0.5, act=act, abits=abits, pool=pool)
+    mode = {"quantized": L.W_QUANT, "binary": L.W_BINARY, "ternary": L.W_TERNARY}[wkind]
+    wfmt = L.WFMT_B1 if kind == "b1" else L.WFMT_I8
+    wp = K.pack_weights(dev(kernel), mode, nb, 1.0, wfmt)
+    wscale = 1.0 / (1 << (nb - 1)) if wkind == "quantized" else 1.0
+    inv = shift = None
+    if bn is not None:
+        i_, s_ = K.bn_constants(*bn, 1e-4)
+        inv, shift = dev(i_), dev(s_)
+    actc = {"quant": L.ACT_QUANT, "binary": L.ACT_SIGN, "leaky": L.ACT_LEAKY, None: L.ACT_NONE}[act]
+    epi = K.make_epilogue(K.acc_scale(xs, wscale), bias=dev(bias) if bias is not None else None, bn_inv=inv, bn_shift=shift,
+                          residual=res_q, res_mul=0.5, act=actc, abits=abits, leaky_alpha=0.3, pool=2 if pool else 0)
+    implc = {"generic": L.IMPL_GENERIC, "auto": L.IMPL_AUTO}[impl]
+    y = K.conv2d(_to_qtensor(K, kind, x, xs, abits), wp, k, k, cout, stride, epi, impl=implc)
+    torch.cuda.synchronize()
+    got = y.data.cpu().numpy()
+    if act == "binary":
+        got = unpack_bits(got, cout)
+    assert got.shape == want.shape
+    if got.dtype == np.float32:
+        assert np.array_equal(got, want.astype(F32)), "max abs diff %g" % np.abs(got - want).max()
+    else:
+        assert np.array_equal(got.astype(np.int32), want.astype(np.int32)), "mismatching levels: %d" % (got != want).sum()
+
+
+@pytest.mark.parametrize("case", [
+    (2, 32, 32, 3, 16, 3, 1, "quantized", 4, "leaky", False),
+    (2, 16, 16, 16, 32, 3, 2, "quantized", 4, "leaky", False),
+    (2, 16, 16, 16, 32, 1, 2, "ternary", 2, None, False),
+    (2, 16, 16, 32, 32, 3, 1, "binary", 1, "leaky", True),
+    (2, 8, 8, 64, 64, 3, 1, "quantized", 4, "quant", False),
+])
+def test_conv2d_float_activations_tolerance(case):
+    """fp32 activations x exact integer weights: accumulation order differs from the float64 oracle, so the
+    bar is the north_star tolerance: max abs error <= 1e-4 relative to the largest |output|."""
+    q, L, K = _mods()
+    n, h, w, cin, cout, k, stride, wkind, nb, act, pool = case
+    rng = np.random.default_rng(_seed(case))
+    x = rng.normal(0, 1, size=(n, h, w, cin)).astype(F32)
+    kernel = rng.uniform(-1, 1, size=(k, k, cin, cout)).astype(F32)
+    fan = k * k * cin
+    bn = (rng.uniform(0.3, 0.9, cout).astype(F32), rng.uniform(-0.2, 0.2, cout).astype(F32),
+          rng.uniform(-0.2, 0.2, cout).astype(F32), (rng.uniform(0.5, 1.5, cout) * fan * 0.3).astype(F32))
+    want, _ = oracle_layer(x, "f32", 1.0, kernel, wkind, nb, 1.0, stride, bn=bn, eps=1e-3, act=act, abits=4, pool=pool)
+    mode = {"quantized": L.W_QUANT, "binary": L.W_BINARY, "ternary": L.W_TERNARY}[wkind]
+    wp = K.pack_weights(dev(kernel), mode, nb, 1.0, L.WFMT_I8)
+    wscale = 1.0 / (1 << (nb - 1)) if wkind == "quantized" else 1.0
+    i_, s_ = K.bn_constants(*bn, 1e-3)
+    actc = {"quant": L.ACT_QUANT, "leaky": L.ACT_LEAKY, None: L.ACT_NONE}[act]
+    epi = K.make_epilogue(F32(wscale), bn_inv=dev(i_), bn_shift=dev(s_), act=actc, abits=4, pool=2 if pool else 0)
+    y = K.conv2d(K.QTensor("f32", dev(x), 1.0, cin), wp, k, k, cout, stride, epi, impl=L.IMPL_GENERIC)
+    got = y.data.cpu().numpy()
+    if act == "quant":
+        # a re-quantised output may flip by one level where the fp32 sum lands on a rounding boundary
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3
+    else:
+        tol = 1e-4 * np.abs(want).max()
+        assert np.abs(got - want).max() <= tol
+
+
+# --------------------------------------------------------------------------- dense head
+@pytest.mark.parametrize("kind,fin,units,wkind,nb,bn,softmax", [
+    ("i8", 4096, 10, "quantized", 4, True, False),
+    ("i8", 576, 10, "quantized", 2, True, False),
+    ("i8", 4096, 10, "quantized", 8, True, False),
+    ("i8", 64, 10, "quantized", 4, False, True),
+    ("i8", 1024, 17, "ternary", 2, True, False),
+    ("b1", 4096, 10, "binary", 1, True, False),
+    ("b1", 256, 32, "binary", 1, False, False),
+    ("f32", 64, 10, "quantized", 4, False, True),
+    ("f32", 300, 10, "binary", 1, True, False),
+])
+def test_dense_head(kind, fin, units, wkind, nb, bn, softmax):
+    q, L, K = _mods()
+    rng = np.random.default_rng(fin * 31 + units)
+    n = 37
+    abits = nb if wkind == "quantized" else 4
+    x, xs = _rand_input(rng, kind, (n, fin), abits)
+    kernel = rng.uniform(-1, 1, size=(fin, units)).astype(F32)
+    bias = rng.uniform(-0.3, 0.3, size=units).astype(F32)
+    bnw = None
+    if bn:
+        bnw = (rng.uniform(0.5, 1.5, units).astype(F32), rng.uniform(-0.2, 0.2, units).astype(F32),
+               rng.uniform(-1, 1, units).astype(F32), (rng.uniform(0.5, 1.5, units) * fan_var(fin, kind)).astype(F32))
+    want, _ = oracle_layer(x, kind, xs, kernel, wkind, nb, 1.0, 1, bias=bias, bn=bnw, eps=1e-4, dense=True)
+    mode = {"quantized": L.W_QUANT, "binary": L.W_BINARY, "ternary": L.W_TERNARY}[wkind]
+    wfmt = L.WFMT_B1 if kind == "b1" else L.WFMT_I8
+    wp = K.pack_weights(dev(kernel), mode, nb, 1.0, wfmt)
+    wscale = 1.0 / (1 << (nb - 1)) if wkind == "quantized" else 1.0
+    inv = shift = None
+    if bnw is not None:
+        i_, s_ = K.bn_constants(*bnw, 1e-4)
+        inv, shift = dev(i_), dev(s_)
+    epi = K.make_epilogue(K.acc_scale(xs if kind != "f32" else 1.0, wscale), bias=dev(bias), bn_inv=inv, bn_shift=shift)
+    out, logits = K.dense(_to_qtensor(K, kind, x, xs, abits), wp, units, epi, softmax=softmax, want_logits=softmax)
+    got = out.cpu().numpy()
+    if softmax:
+        lg = logits.cpu().numpy()
+        if kind == "f32":
+            assert np.abs(lg - want).max() <= 1e-4 * np.abs(want).max()
+        else:
+            assert np.array_equal(lg, want)
+        assert np.abs(got - exact.softmax64(lg)).max() <= 2e-6
+        assert np.array_equal(got.argmax(1), lg.argmax(1))
+    elif kind == "f32":
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+    else:
+        assert np.array_equal(got, want)
+
+
+def fan_var(fin, kind):
+    return fin * (1.0 if kind == "b1" else 0.11)
+
+
+# --------------------------------------------------------------------------- stand-alone fp32 ops
+def test_standalone_ops():
+    q, L, K = _mods()
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 0.6, size=(5, 6, 8, 70)).astype(F32)
+    x.reshape(-1)[:6] = [0.0, 2.0 ** -24, 0.0625, -0.0625, 0.1875, 5.0]
+    for ab in (2, 4, 8):
+        got = K.quantize_act(dev(x), ab)
+        assert np.array_equal(got.data.cpu().numpy().astype(np.int32), exact.act_quant_levels(x, ab))
+        assert np.array_equal(got.to_float().cpu().numpy(), exact.act_quant_levels(x, ab).astype(F32) * F32(1 / (1 << (ab - 1))))
+    sb = K.sign_act(dev(x))
+    assert np.array_equal(sb.data.cpu().numpy().astype(np.uint32), exact.pack_bits_lastdim(exact.act_binary_levels(x)))
+    assert np.array_equal(sb.to_float().cpu().numpy(), exact.act_binary_levels(x).astype(F32))
+    inv = rng.uniform(0.5, 1.5, 70).astype(F32)
+    shift = rng.uniform(-1, 1, 70).astype(F32)
+    want = ((x * inv).astype(F32) + shift).astype(F32)
+    assert np.array_equal(K.batchnorm(dev(x), dev(inv), dev(shift)).cpu().numpy(), want)
+    assert np.array_equal(K.maxpool2(dev(x)).cpu().numpy(), exact.maxpool2(x))
+    assert np.array_equal(K.leaky(dev(x), 0.3).cpu().numpy(), exact.leaky(x))
+
+
+def test_empty_batch_and_errors():
+    q, L, K = _mods()
+    wp = K.pack_weights(dev(np.zeros((3, 3, 4, 8), F32)), L.W_QUANT, 4, 1.0, L.WFMT_I8)
+    epi = K.make_epilogue(1.0, act=L.ACT_QUANT, abits=4)
+    y = K.conv2d(K.QTensor("i8", torch.zeros((0, 8, 8, 4), dtype=torch.int8, device="cuda"), 0.125, 4), wp, 3, 3, 8, 1, epi)
+    assert tuple(y.data.shape) == (0, 8, 8, 8)
+    with pytest.raises(L.QnnbError):
+        K.conv2d(K.QTensor("i8", torch.zeros((1, 8, 8, 4), dtype=torch.int8, device="cuda"), 0.125, 4), wp, 3, 3, 8, 3, epi)
+    with pytest.raises(L.QnnbError):
+        K.pack_weights(dev(np.zeros((3, 3, 4, 8), F32)), L.W_QUANT, 16, 1.0, L.WFMT_I8)
+    with pytest.raises(L.QnnbError) as ei:
+        K.conv2d(K.QTensor("i8", torch.zeros((1, 9, 9, 4), dtype=torch.int8, device="cuda"), 0.125, 4), wp, 3, 3, 8, 1, epi,
+                 impl=L.IMPL_TCGEN05)
+    assert ei.value.code == L.EUNSUPPORTED
