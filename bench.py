@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the CIFAR-10 VGG full-qnn w4a4 forward (BASELINE.json
+configs[2], batch 1024 per GPU) through the fused plan; one JSON line on stdout (rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle O2a)
+
+A *step* is one forward pass of the hot path over one batch.  Batches are independent, so N
+GPUs run N shards with no data-path collective except the final logit all-gather (NCCL), which
+is inside the timed region; scaling is weak (1024 images per GPU per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "images/sec CIFAR-10 VGG full-qnn w4a4 inference (whole job)"
+WORKLOADS = {
+    # name -> (config kwargs, batch per GPU)
+    "cfg3": (dict(network_type='full-qnn', wbits=4, abits=4, architecture='VGG', nla=1, nfa=64, nlb=1, nfb=128, nlc=1, nfc=256), 1024),
+    "cfg4": (dict(network_type='full-qnn', wbits=8, abits=8, architecture='VGG', nla=3, nfa=256, nlb=3, nfb=256, nlc=3, nfc=256), 4096),
+    "cfg2": (dict(network_type='full-bnn', architecture='VGG', nla=1, nfa=64, nlb=1, nfb=128, nlc=1, nfc=256), 256),
+    "cfg1": (dict(network_type='full-qnn', wbits=2, abits=2, architecture='VGG', dataset='MNIST', dim=28, channels=1,
+                  nla=1, nfa=64, nlb=1, nfb=64, nlc=1, nfc=64), 100),
+}
+
+
+def make_cf(**kw):
+    base = dict(network_type='full-qnn', wbits=4, abits=4, architecture='VGG', dataset='CIFAR-10', dim=32,
+                channels=3, classes=10, nla=1, nfa=64, nlb=1, nfb=128, nlc=1, nfc=256, nres=3, pfilt=1,
+                kernel_initializer='glorot_uniform', kernel_regularizer=0.)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def int8_peak_tops(pk):
+    """Dense int8 tensor-core ceiling.  A tcgen05 kind::i8 micro-benchmark result (tools/) overrides the
+    provisional 2 x measured bf16."""
+    p = os.path.join(ROOT, "profiles", "int8_peak.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["int8_tops"]), "measured tcgen05 kind::i8 micro-benchmark"
+    return 2.0 * pk["bf16_tflops"], "2 x %s bf16 burst (provisional)" % pk["source"]
+
+
+# ------------------------------------------------------------------------------ algorithmic work
+def layer_work(cf, batch):
+    """Per fused step: (name, ops, bytes) with ops = 2*MACs (no padding) and bytes = input + output at
+    deployed width + packed weights."""
+    out = []
+    h = cf.dim
+    cin = cf.channels
+    in_bytes_per = 1
+    blocks = [(max(cf.nla, 1), cf.nfa), (cf.nlb, cf.nfb), (cf.nlc, cf.nfc)]
+    li = 0
+    for nl, nf in blocks:
+        for j in range(nl):
+            pooled = (j == nl - 1)
+            macs = batch * h * h * 9 * cin * nf
+            oh = h // 2 if pooled else h
+            byts = batch * h * h * cin * in_bytes_per + batch * oh * oh * nf + 9 * cin * nf
+            out.append(("conv%d" % li, 2 * macs, byts))
+            li += 1
+            cin = nf
+            h = oh
+    feat = h * h * cin
+    out.append(("dense", 2 * batch * feat * cf.classes, batch * feat + batch * cf.classes * 4 + feat * cf.classes))
+    return out
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([s.strip() for s in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def build_spec(cfkw, seed=42):
+    from oracle import netspec
+    cf = make_cf(**cfkw)
+    nodes = netspec.build_spec(cf)
+    netspec.set_weights(nodes, netspec.random_weights(nodes, seed=seed, bias_range=0.1, bn="spread"))
+    return cf, nodes
+
+
+def cpu_reference_rate(nodes, cf, sample, repeats=3, warm=1):
+    """images/sec of the reference's forward (oracle O2a: fp32, per-forward quantise, scaling identity,
+    un-fused BN / activation / pooling) on all host cores."""
+    import torch
+    from oracle import refstate
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = np.random.default_rng(99).integers(0, 256, size=(sample, cf.dim, cf.dim, cf.channels), dtype=np.uint8)
+    for _ in range(warm):
+        refstate.forward(nodes, x, trick=True)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        refstate.forward(nodes, x, trick=True)
+        ts.append(time.perf_counter() - t0)
+    return sample / float(np.median(ts)), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfkw, batch = WORKLOADS[args.workload]
+    cf, nodes = build_spec(cfkw)
+    sample = min(batch, args.ref_sample)
+    import torch
+    from oracle import refstate
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = np.random.default_rng(99).integers(0, 256, size=(sample, cf.dim, cf.dim, cf.channels), dtype=np.uint8)
+    for _ in range(args.warmup):
+        refstate.forward(nodes, x, trick=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        refstate.forward(nodes, x, trick=True)
+    dt = time.perf_counter() - t0
+    rate = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: CIFAR-10 VGG %s w%da%d, reference CPU forward" % (args.workload, cf.network_type, cf.wbits, cf.abits),
+                       "sample_images_per_step": sample},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d images per step (oracle O2a: torch-CPU fp32 restatement of the reference graph)" % sample},
+            "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import qnn_b200 as q
+    from helpers import assign_weights_from_spec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    cfkw, batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    cf, nodes = build_spec(cfkw)
+    q.reset_names()
+    model = q.build_model(cf)
+    assign_weights_from_spec(model, nodes)
+    impl = {"auto": 0, "generic": 1, "tcgen05": 2}[args.kernels]
+    plan = model.plan(impl)
+
+    # ---- synthetic inputs: NBUF distinct resident batches, total > L2 (126 MB), rotated every step
+    img_bytes = cf.dim * cf.dim * cf.channels
+    nbuf = max(4, int(np.ceil(160e6 / (batch * img_bytes))))
+    rng = np.random.default_rng(1234 + rank)
+    host = [torch.from_numpy(rng.integers(0, 256, size=(batch, cf.dim, cf.dim, cf.channels), dtype=np.uint8)).pin_memory()
+            for _ in range(min(nbuf, 8))]
+    bufs = [host[i % len(host)].to(dev) for i in range(nbuf)]
+    gather = [torch.empty((batch, cf.classes), dtype=torch.float32, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_fn(xb):
+        out = plan.forward(xb)
+        if world > 1:
+            dist.all_gather(gather, out)
+        return out
+
+    # warm-up (also packs weights / uploads constants)
+    plan.launches = 0
+    out0 = step_fn(bufs[0])
+    launches_per_step = plan.launches
+    torch.cuda.synchronize()
+
+    # ---- parity spot-check of the benchmarked configuration against the exact oracle (small slice)
+    from oracle import exact
+    xs = host[0][:8].numpy()
+    ok = bool(np.array_equal(model.predict(xs, impl=impl), exact.forward(nodes, xs)))
+
+    # ---- CUDA graphs: one per input buffer, sharing a memory pool
+    graphs = None
+    if args.graphs and world == 1:
+        graphs = []
+        pool = torch.cuda.graph_pool_handle()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for b in bufs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=s):
+                    o = plan.forward(b)
+                graphs.append((g, o))
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % nbuf][0].replay()
+        else:
+            step_fn(bufs[i % nbuf])
+
+    for i in range(max(args.warmup, 3)):
+        run_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(args.steps):
+            run_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        time.sleep(0.25)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = batch * world * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing (CUDA events between launches, same rotating inputs) for the roofline
+    work = layer_work(cf, batch)
+    per = np.zeros(len(plan.steps))
+    reps = max(5, min(args.steps, 50))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(plan.steps) + 1)] for _ in range(reps)]
+    from qnn_b200 import kernels as K
+    for r in range(reps):
+        env = {plan.input_idx: K.as_qtensor(bufs[(r + 3) % nbuf])}
+        evs[r][0].record()
+        for si, st in enumerate(plan.steps):
+            (plan._run_conv if st.kind == "conv" else plan._run_dense)(st, env)
+            evs[r][si + 1].record()
+    torch.cuda.synchronize()
+    for r in range(reps):
+        for si in range(len(plan.steps)):
+            per[si] += evs[r][si].elapsed_time(evs[r][si + 1]) / reps
+    dom = int(np.argmax(per))
+    pk = peaks()
+    name, ops, byts = work[dom]
+    i8_peak, i8_src = int8_peak_tops(pk)
+    ai = ops / byts
+    tensor_bound = ai > (i8_peak * 1e12) / (pk["hbm_gbs"] * 1e9)
+    if tensor_bound:
+        achieved = ops / (per[dom] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s", "frac": achieved / i8_peak,
+                "traffic": None, "kernel": name, "kernel_ms": float(per[dom]), "peak_source": i8_src}
+    else:
+        achieved = byts / (per[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                "traffic": None, "kernel": name, "kernel_ms": float(per[dom]), "peak_source": pk["source"] + " copy bandwidth"}
+    roof["per_kernel_ms"] = {w[0]: float(p) for w, p in zip(work, per)}
+
+    # ---- end to end through the public API: pinned host batch -> predict -> host logits, every step
+    torch.cuda.synchronize()
+    for i in range(3):
+        model.predict(host[i % len(host)], impl=impl)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = model.predict(host[i % len(host)], impl=impl)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = batch * world * args.steps / float(te.item())
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample = min(batch, args.ref_sample)
+            rate, cores = cpu_reference_rate(nodes, cf, sample)
+            cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "%d images, median of 3 (oracle O2a: torch-CPU fp32 restatement of the reference graph)" % sample}
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 (int32 accumulate, fp32 epilogue)", "data": "synthetic",
+                "config": {"workload": "%s: CIFAR-10 VGG %s w%da%d %d/%d/%d x %d/%d/%d, batch %d per GPU" % (
+                               args.workload, cf.network_type, cf.wbits, cf.abits, cf.nla, cf.nlb, cf.nlc, cf.nfa, cf.nfb, cf.nfc, batch),
+                           "global_batch": batch * world, "parallelism": "batch-sharded x%d, NCCL logit all-gather" % world,
+                           "l2_policy": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotated every step" % (nbuf, nbuf * batch * img_bytes / 1e6),
+                           "cuda_graphs": graphs is not None, "kernels": args.kernels,
+                           "parity_vs_exact_oracle": ok},
+                "clocks": clk.summary(), "gpu_launches": launches_per_step * args.steps,
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": batch * img_bytes,
+                        "d2h_bytes_per_step": batch * cf.classes * 4},
+                "roofline": roof}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--kernels", default="auto", choices=["auto", "generic", "tcgen05"])
+    ap.add_argument("--graphs", type=int, default=1)
+    ap.add_argument("--ref-sample", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,10 +97,11 @@ int qnnb_conv2d_out_shape(const qnnb_conv_desc* d, int32_t* oh, int32_t* ow) {
 }
 
 int qnnb_conv2d(const qnnb_conv_desc* d, const void* x, const void* w, void* y, void* stream) {
-  QNNB_CHECK_ARG(d && x && w && y, "conv2d: null pointer");
+  QNNB_CHECK_ARG(d, "conv2d: null descriptor");
   int rc = validate_conv(*d);
   if (rc) return rc;
-  if (d->n == 0) return QNNB_OK;
+  if (d->n == 0) return QNNB_OK;           /* empty batch: nothing to launch, pointers may be null */
+  QNNB_CHECK_ARG(x && w && y, "conv2d: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const char* why = "";
   const bool tc_ok = conv_tc_supported(*d, &why);
@@ -114,8 +115,9 @@ int qnnb_conv2d(const qnnb_conv_desc* d, const void* x, const void* w, void* y, 
 }
 
 int qnnb_dense(const qnnb_dense_desc* d, const void* x, const void* w, float* y, float* logits, void* stream) {
-  QNNB_CHECK_ARG(d && x && w && y, "dense: null pointer");
+  QNNB_CHECK_ARG(d, "dense: null descriptor");
   QNNB_CHECK_ARG(d->n >= 0 && d->fin > 0 && d->units > 0, "dense: bad shape n=%d fin=%d units=%d", d->n, d->fin, d->units);
+  QNNB_CHECK_ARG(d->n == 0 || (x && w && y), "dense: null pointer");
   QNNB_CHECK_ARG(d->in_kind == QNNB_KIND_I8 || d->in_kind == QNNB_KIND_B1 || d->in_kind == QNNB_KIND_F32, "dense: bad in_kind %d", d->in_kind);
   int rc = validate_epilogue(d->epi, false, false);
   if (rc) return rc;

@@ -100,6 +100,8 @@ def make_epilogue(acc_scale, bias=None, bn_inv=None, bn_shift=None, residual: QT
     e.abits = int(abits)
     e.leaky_alpha = float(F32(leaky_alpha))
     e.pool = int(pool)
+    # the struct only holds raw device pointers: keep the tensors alive as long as the struct is
+    e._refs = (bias, bn_inv, bn_shift, residual)
     return e
 
 

@@ -266,14 +266,14 @@ class Plan:
 
     def predict(self, x, batch_size=None, return_logits=False):
         as_numpy = isinstance(x, np.ndarray)
-        if as_numpy:
+        host_tensor = (not as_numpy) and isinstance(x, torch.Tensor) and not x.is_cuda
+        if as_numpy or host_tensor:
             if not torch.cuda.is_available():
                 raise RuntimeError("predict needs a CUDA device: this package has no CPU path")
-            xt = torch.from_numpy(np.ascontiguousarray(x)).cuda(non_blocking=True)
+            src = torch.from_numpy(np.ascontiguousarray(x)) if as_numpy else x.contiguous()
+            xt = src.cuda(non_blocking=True)          # asynchronous when the host buffer is pinned
         else:
             xt = x
-        if not xt.is_cuda:
-            raise RuntimeError("predict needs a CUDA tensor: this package has no CPU path")
         n = int(xt.shape[0])
         bs = int(batch_size) if batch_size else min(max(n, 1), MAX_CHUNK)
         outs, logs = [], []
@@ -290,7 +290,10 @@ class Plan:
         else:
             out = torch.cat(outs) if len(outs) > 1 else outs[0]
             logit = (torch.cat(logs) if len(logs) > 1 else logs[0]) if return_logits else None
-        if as_numpy:
-            out = out.cpu().numpy()
-            logit = logit.cpu().numpy() if logit is not None else None
+        if as_numpy or host_tensor:
+            out = out.cpu()
+            logit = logit.cpu() if logit is not None else None
+            if as_numpy:
+                out = out.numpy()
+                logit = logit.numpy() if logit is not None else None
         return (out, logit) if return_logits else out
