@@ -1,8 +1,452 @@
-// placeholder until the tcgen05 kernel lands
+// K1 -- 3x3 stride-1 SAME int8 convolution as an implicit GEMM on the 5th-gen tensor cores:
+// TMA-staged NHWC tiles -> tcgen05.mma kind::i8 -> int32 accumulators in TMEM -> fused epilogue.
+//
+// Stands in for K.conv2d + bias_add + BatchNormalization + quantized_tanh (+ MaxPooling2D) of
+// QuantizedConv2D.call (layers/quantized_layers.py:164-194) as chained by models/vgg.py:15-37.
+//
+// Orientation: D[channel][pixel] = W[channel][K] * X[pixel][K]^T, i.e. the WEIGHTS are the MMA's A
+// operand (M = 128 output channels) and the ACTIVATIONS the B operand (N = 256 output pixels), both
+// K-major.  TMEM lane = output channel, TMEM column = pixel, so an epilogue thread owns ONE channel:
+// its bias / BN constants live in registers and the 2x2 max-pool is an in-register reduction over
+// columns (done on the raw accumulators: every epilogue step is monotone, see conv_generic.cu).
+//
+// Implicit GEMM: K = 9 taps x Cin.  For tap (r,s) and channel chunk c0 the B tile is ONE 4-D TMA box
+// {KC, TW, TH, TN} of the NHWC tensor at (c0, w0+s-1, h0+r-1, n0): out-of-bounds rows/columns are
+// zero-filled by the TMA unit, which IS the SAME padding.  The box lands as 256 rows of KC bytes with
+// the 64B/128B swizzle the UMMA shared-memory descriptor expects.  The A tile is a 2-D box
+// {KC, 128} of the packed kernel [Cout][9*Cin].
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (two warps per TMEM lane quarter, each takes half of the columns).
+// Pipelines: smem ring full/empty (TMA <-> MMA), 2 TMEM accumulators full/empty (MMA <-> epilogue),
+// persistent static tile schedule.
 #include "common.cuh"
+
+#include <cuda.h>
+
 namespace qnnb {
-bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) { *why = "tcgen05 path not built"; return false; }
+
+namespace {
+
+constexpr int TILE_M = 128;   // output channels per tile (UMMA M)
+constexpr int TILE_N = 256;   // output pixels per tile   (UMMA N)
+constexpr int UMMA_K = 32;    // int8
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) __trap();     // a broken pipeline must fault, not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 64 consecutive columns: thread t of the warp receives lane (base_lane + t), columns c..c+63
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, int (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]),
+        "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]),
+        "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]),
+        "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand whose rows are KC bytes wide and stored with the
+// KC-byte swizzle (KC = 64 or 128): 8-row groups are 8*KC bytes apart (SBO); LBO is unused for swizzled
+// K-major layouts (set to 16 B); version = 1 (Blackwell); layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+template <int KC>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = (KC == 128) ? 2ull : 4ull;
+  constexpr uint64_t sbo = (8 * KC) >> 4;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= sbo << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+// instruction descriptor: dense, S32 accumulate, A = B = signed int8, both K-major, N = 256, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed, bool b_signed) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  int n, h, w, cin, cout;
+  int tiles_w, tiles_h, tiles_n, m_tiles, num_tiles;
+  int kchunks;            // cin / KC
+  void* y;
+  Epi epi;
+};
+
+template <int KC, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = TILE_M * KC;
+  static constexpr int B_BYTES = TILE_N * KC;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+};
+
+// ------------------------------------------------------------------ the kernel
+// TW in {32, 16, 8} selects the pixel-tile geometry {TH, TW, TN}: {8,32,1}, {16,16,1}, {8,8,4}.
+template <int KC, int STAGES, int TW, bool POOL, bool OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+  constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
+  constexpr int TN = (TW == 8) ? 4 : 1;
+  static_assert(TH * TW * TN == TILE_N, "tile geometry");
+  using SL = SmemLayout<KC, STAGES>;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + SL::BAR_OFFSET;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SL::BAR_OFFSET + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int ksteps = 9 * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles;
+        int pt = tile / p.m_tiles;
+        const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
+        const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
+        const int n0 = pt * TN, h0 = th_i * TH, w0 = tw_i * TW;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = ks / p.kchunks, kc = ks % p.kchunks;
+          const int r = tap / 3, s = tap % 3;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * SL::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + SL::A_BYTES;
+          mbar_expect_tx(full_bar(stage), SL::STAGE_BYTES);
+          tma_load_2d(a_dst, &map_w, full_bar(stage), tap * p.cin + kc * KC, mt * TILE_M);
+          tma_load_4d(b_dst, &map_x, full_bar(stage), kc * KC, w0 + s - 1, h0 + r - 1, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, true, true);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TILE_N);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * SL::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + SL::A_BYTES;
+          const uint64_t a_desc = make_smem_desc<KC>(a_addr);
+          const uint64_t b_desc = make_smem_desc<KC>(b_addr);
+#pragma unroll
+          for (int k = 0; k < KC / UMMA_K; ++k) {
+            // advance both descriptors by k*32 bytes inside the swizzle atom (start-address field is in 16 B units)
+            umma_i8(d_tmem, a_desc + (uint64_t)(k * (UMMA_K >> 4)), b_desc + (uint64_t)(k * (UMMA_K >> 4)), idesc,
+                    (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));                      // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
+    const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
+    const int ch_in_tile = quarter * 32 + lane;
+    const Epi& e = p.epi;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile % p.m_tiles;
+      int pt = tile / p.m_tiles;
+      const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
+      const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
+      const int n0 = pt * TN, h0 = th_i * TH, w0 = tw_i * TW;
+      const int ch = mt * TILE_M + ch_in_tile;
+      const ChanConst cc = load_chan(e, ch, ch < p.cout);
+      const bool dec = decreasing(cc);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const int col0 = half * 128 + j * 64;
+        int v[64];
+        tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + col0), v);
+        tmem_ld_wait();
+        if (j == 1) {
+          // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        // 64 columns = rows [row0, row0 + 64/TW) of image n0 + img
+        const int img = col0 / (TH * TW);
+        const int row0 = (col0 % (TH * TW)) / TW;
+        const int nimg = n0 + img;
+        if (nimg >= p.n) continue;
+        if constexpr (POOL) {
+          constexpr int PR = 64 / TW / 2, PC = TW / 2;
+          const int oh_dim = p.h >> 1, ow_dim = p.w >> 1;
+          int8_t* ybase = (int8_t*)p.y + (((long long)nimg * oh_dim + ((h0 + row0) >> 1)) * ow_dim + (w0 >> 1)) * p.cout + ch;
+#pragma unroll
+          for (int pr = 0; pr < PR; ++pr) {
+#pragma unroll
+            for (int pc = 0; pc < PC; ++pc) {
+              const int i00 = (2 * pr) * TW + 2 * pc;
+              const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
+              const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
+              const float z = affine((float)(dec ? mn : mx), cc);
+              ybase[((long long)pr * ow_dim + pc) * p.cout] = (int8_t)act_quant(z, e.qm);
+            }
+          }
+        } else {
+          constexpr int R = 64 / TW;
+          const long long pix0 = ((long long)nimg * p.h + (h0 + row0)) * p.w + w0;
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+            for (int c = 0; c < TW; ++c) {
+              const float z = affine((float)v[rr * TW + c], cc);
+              const long long off = (pix0 + (long long)rr * p.w + c) * p.cout + ch;
+              if constexpr (OUT_F32) ((float*)p.y)[off] = z;
+              else ((int8_t*)p.y)[off] = (int8_t)act_quant(z, e.qm);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+struct Geometry { int tw, th, tn; };
+
+bool pick_geometry(int h, int w, Geometry* g) {
+  if (w == 32 && h % 8 == 0) { *g = {32, 8, 1}; return true; }
+  if (w == 16 && h % 16 == 0) { *g = {16, 16, 1}; return true; }
+  if (w == 8 && h == 8) { *g = {8, 8, 4}; return true; }
+  return false;
+}
+
+template <int KC, int STAGES, int TW, bool POOL, bool OUT_F32>
+int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int grid, cudaStream_t st) {
+  auto kern = conv3x3_i8_tc_kernel<KC, STAGES, TW, POOL, OUT_F32>;
+  constexpr int smem = SmemLayout<KC, STAGES>::TOTAL;
+  QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, NUM_THREADS, smem, st>>>(mw, mx, p);
+  QNNB_CUDA(cudaGetLastError());
+  return QNNB_OK;
+}
+
+template <int KC, int STAGES, int TW>
+int launch_tw(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int grid, bool pool, bool f32, cudaStream_t st) {
+  if (f32) return launch_variant<KC, STAGES, TW, false, true>(mw, mx, p, grid, st);
+  if (pool) return launch_variant<KC, STAGES, TW, true, false>(mw, mx, p, grid, st);
+  return launch_variant<KC, STAGES, TW, false, false>(mw, mx, p, grid, st);
+}
+
+template <int KC, int STAGES>
+int launch_kc(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int grid, int tw, bool pool, bool f32, cudaStream_t st) {
+  if (tw == 32) return launch_tw<KC, STAGES, 32>(mw, mx, p, grid, pool, f32, st);
+  if (tw == 16) return launch_tw<KC, STAGES, 16>(mw, mx, p, grid, pool, f32, st);
+  return launch_tw<KC, STAGES, 8>(mw, mx, p, grid, pool, f32, st);
+}
+
+}  // namespace
+
+bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
+  Geometry g;
+  if (d.in_kind != QNNB_KIND_I8) { *why = "input must be int8 levels"; return false; }
+  if (d.kh != 3 || d.kw != 3 || d.stride != 1) { *why = "only 3x3 stride 1"; return false; }
+  if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
+  if (d.cout % 128 != 0) { *why = "Cout must be a multiple of 128"; return false; }
+  if (!pick_geometry(d.h, d.w, &g)) { *why = "spatial size must be 32xH(H%8==0), 16x16k or 8x8"; return false; }
+  if (d.epi.res_kind != QNNB_KIND_NONE) { *why = "residual epilogue not on the tensor-core path"; return false; }
+  if (d.epi.act == QNNB_ACT_QUANT) return true;
+  if (d.epi.act == QNNB_ACT_NONE && d.epi.pool == 0) return true;
+  *why = "epilogue must be quantized_tanh (optionally pooled) or plain fp32";
+  return false;
+}
+
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
-  set_error("tcgen05 path not built"); return QNNB_EUNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
+  Geometry g;
+  pick_geometry(d.h, d.w, &g);
+  const int KC = (d.cin % 128 == 0) ? 128 : 64;
+  const CUtensorMapSwizzle swz = (KC == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+  CUtensorMap mw, mx;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * d.cin, (cuuint64_t)d.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * d.cin};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)TILE_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return QNNB_ECUDA; }
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+    cuuint64_t strides[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.w * d.cin, (cuuint64_t)d.h * d.w * d.cin};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(activations) failed with %d", (int)r); return QNNB_ECUDA; }
+  }
+
+  TcParams p;
+  p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
+  p.tiles_w = d.w / g.tw;
+  p.tiles_h = d.h / g.th;
+  p.tiles_n = ceil_div(d.n, g.tn);
+  p.m_tiles = d.cout / TILE_M;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.m_tiles;
+  p.kchunks = d.cin / KC;
+  p.y = y;
+  p.epi = make_epi(d.epi);
+
+  int dev = 0, sms = 0;
+  QNNB_CUDA(cudaGetDevice(&dev));
+  QNNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const bool pool = d.epi.pool == 2;
+  const bool f32 = d.epi.act == QNNB_ACT_NONE;
+  if (KC == 128) return launch_kc<128, 4>(mw, mx, p, grid, g.tw, pool, f32, st);
+  return launch_kc<64, 6>(mw, mx, p, grid, g.tw, pool, f32, st);
 }
-}
+
+}  // namespace qnnb

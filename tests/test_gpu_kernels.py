@@ -308,3 +308,57 @@ def test_empty_batch_and_errors():
         K.conv2d(K.QTensor("i8", torch.zeros((1, 9, 9, 4), dtype=torch.int8, device="cuda"), 0.125, 4), wp, 3, 3, 8, 1, epi,
                  impl=L.IMPL_TCGEN05)
     assert ei.value.code == L.EUNSUPPORTED
+
+
+# --------------------------------------------------------------------------- tcgen05 implicit-GEMM conv (K1)
+TC_CASES = [
+    # n, h, w, cin, cout, nb, abits, pool, f32_out
+    (1, 16, 16, 64, 128, 4, 4, False, True),      # raw accumulators, one tile
+    (3, 16, 16, 64, 128, 4, 4, True, False),      # cfg3 layer 2
+    (5, 8, 8, 128, 256, 4, 4, True, False),       # cfg3 layer 3, ragged image group (5 = 4 + 1)
+    (2, 32, 32, 256, 256, 8, 8, False, False),    # cfg4 block A interior layer
+    (2, 32, 32, 256, 256, 8, 8, True, False),     # cfg4 block A last layer
+    (3, 16, 16, 256, 256, 8, 8, False, False),
+    (9, 8, 8, 256, 256, 8, 8, True, False),
+    (2, 32, 32, 64, 128, 2, 2, True, False),
+    (40, 16, 16, 128, 128, 4, 4, False, False),   # more tiles than one wave at grid = #SM? (40 tiles) exercises the ring
+    (700, 8, 8, 64, 128, 4, 4, True, False),      # 175 tiles > 148 SMs: persistent loop, both TMEM accumulators
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=["n%d_%dx%d_%d-%d_w%da%d%s%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_pool" if c[7] else "", "_f32" if c[8] else "") for c in TC_CASES])
+def test_conv2d_tcgen05_bit_exact(case):
+    q, L, K = _mods()
+    n, h, w, cin, cout, nb, abits, pool, f32_out = case
+    rng = np.random.default_rng(_seed(case))
+    x, xs = _rand_input(rng, "i8", (n, h, w, cin), abits)
+    kernel = rng.uniform(-1, 1, size=(3, 3, cin, cout)).astype(F32)
+    fan = 9 * cin
+    wp = K.pack_weights(dev(kernel), L.W_QUANT, nb, 1.0, L.WFMT_I8)
+    if f32_out:
+        # scale 1, no bias / BN: the fp32 output IS the int32 accumulator (|acc| < 2^24 here)
+        epi = K.make_epilogue(1.0, act=L.ACT_NONE)
+        y = K.conv2d(K.QTensor("i8", dev(x), xs, cin), wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05)
+        torch.cuda.synchronize()
+        got = y.data.cpu().numpy()
+        lv = exact.quantize_levels(kernel, nb)
+        want = exact.conv_accumulate(x.astype(np.int64), lv, 1).astype(F32)
+        bad = np.argwhere(got != want)
+        assert bad.shape[0] == 0, "accumulator mismatches: %d of %d, first %s got %s want %s" % (
+            bad.shape[0], want.size, bad[:5].tolist(), [got[tuple(b)] for b in bad[:5]], [want[tuple(b)] for b in bad[:5]])
+        return
+    bias = rng.uniform(-0.3, 0.3, size=cout).astype(F32)
+    bn = (rng.uniform(0.3, 0.9, cout).astype(F32) * rng.choice([1, 1, -1], cout).astype(F32),
+          rng.uniform(-0.2, 0.2, cout).astype(F32),
+          (rng.uniform(-0.2, 0.2, cout) * np.sqrt(fan * 0.11)).astype(F32),
+          (rng.uniform(0.5, 1.5, cout) * fan * 0.11).astype(F32))
+    want, _ = oracle_layer(x, "i8", xs, kernel, "quantized", nb, 1.0, 1, bias=bias, bn=bn, eps=1e-4, act="quant", abits=abits, pool=pool)
+    i_, s_ = K.bn_constants(*bn, 1e-4)
+    epi = K.make_epilogue(K.acc_scale(xs, 1.0 / (1 << (nb - 1))), bias=dev(bias), bn_inv=dev(i_), bn_shift=dev(s_),
+                          act=L.ACT_QUANT, abits=abits, pool=2 if pool else 0)
+    y = K.conv2d(K.QTensor("i8", dev(x), xs, cin), wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    got = y.data.cpu().numpy().astype(np.int32)
+    assert got.shape == want.shape
+    bad = np.argwhere(got != want)
+    assert bad.shape[0] == 0, "level mismatches: %d of %d, first %s" % (bad.shape[0], want.size, bad[:8].tolist())
