@@ -282,20 +282,33 @@ def run_ours(args):
 
     # ---- per-kernel timing (CUDA events between launches, same rotating inputs) for the roofline
     work = layer_work(cf, batch)
+    # Each kernel is replayed REPS times from its own CUDA graph (no host launch gaps) on the activations
+    # the previous layer produced, alternating between two independent forward environments.
     per = np.zeros(len(plan.steps))
-    reps = max(5, min(args.steps, 50))
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(plan.steps) + 1)] for _ in range(reps)]
     from qnn_b200 import kernels as K
-    for r in range(reps):
-        env = {plan.input_idx: K.as_qtensor(bufs[(r + 3) % nbuf])}
-        evs[r][0].record()
-        for si, st in enumerate(plan.steps):
-            (plan._run_conv if st.kind == "conv" else plan._run_dense)(st, env)
-            evs[r][si + 1].record()
+    REPS = 10
+    envs = [plan.run(bufs[i]) for i in range(2)]
     torch.cuda.synchronize()
-    for r in range(reps):
-        for si in range(len(plan.steps)):
-            per[si] += evs[r][si].elapsed_time(evs[r][si + 1]) / reps
+    side = torch.cuda.Stream()
+    for si, st in enumerate(plan.steps):
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for r in range(REPS):
+                    env = dict(envs[r % 2])
+                    (plan._run_conv if st.kind == "conv" else plan._run_dense)(st, env)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        per[si] = a.elapsed_time(b) / (3 * REPS)
+        del g
     dom = int(np.argmax(per))
     pk = peaks()
     name, ops, byts = work[dom]

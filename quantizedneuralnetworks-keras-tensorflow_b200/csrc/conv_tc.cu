@@ -158,6 +158,94 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
+// ------------------------------------------------------------------ epilogue role (shared by K1 and K5)
+// Warp `warp` (4..11) drains TMEM lanes 32*(warp%4).. of both accumulators: thread = one output channel,
+// columns = the 256 pixels of the tile in {TN, TH, TW} order.  Fixed fp32 op order of common.cuh.
+template <int TW, bool POOL, bool OUT_F32>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              int warp, int lane) {
+  constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
+  constexpr int TN = (TW == 8) ? 4 : 1;
+  const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
+  const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
+  const int ch_in_tile = quarter * 32 + lane;
+  const Epi& e = p.epi;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int mt = tile % p.m_tiles;
+    int pt = tile / p.m_tiles;
+    const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
+    const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
+    const int n0 = pt * TN, h0 = th_i * TH, w0 = tw_i * TW;
+    const int ch = mt * TILE_M + ch_in_tile;
+    const bool ch_ok = ch < p.cout;
+    const bool warp_active = (mt * TILE_M + quarter * 32) < p.cout;      // warp-uniform
+    const ChanConst cc = load_chan(e, ch, ch_ok);
+    const bool dec = decreasing(cc);
+    const int acc = it & 1;
+    const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    if (!warp_active) {
+      // this lane quarter holds only padding channels: nothing to read
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+      continue;
+    }
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      const int col0 = half * 128 + j * 64;
+      int v[64];
+      __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
+      tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + col0), v);
+      tmem_ld_wait();
+      if (j == 1) {
+        // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+      }
+      // 64 columns = rows [row0, row0 + 64/TW) of image n0 + img
+      const int img = col0 / (TH * TW);
+      const int row0 = (col0 % (TH * TW)) / TW;
+      const int nimg = n0 + img;
+      if (nimg >= p.n) continue;               // warp-uniform (ragged last image group)
+      if constexpr (POOL) {
+        constexpr int PR = 64 / TW / 2, PC = TW / 2;
+        const int oh_dim = p.h >> 1, ow_dim = p.w >> 1;
+        int8_t* ybase = (int8_t*)p.y + (((long long)nimg * oh_dim + ((h0 + row0) >> 1)) * ow_dim + (w0 >> 1)) * p.cout + ch;
+#pragma unroll
+        for (int pr = 0; pr < PR; ++pr) {
+#pragma unroll
+          for (int pc = 0; pc < PC; ++pc) {
+            const int i00 = (2 * pr) * TW + 2 * pc;
+            const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
+            const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
+            const float z = affine((float)(dec ? mn : mx), cc);
+            if (ch_ok) ybase[((long long)pr * ow_dim + pc) * p.cout] = (int8_t)act_quant(z, e.qm);
+          }
+        }
+      } else {
+        constexpr int R = 64 / TW;
+        const long long pix0 = ((long long)nimg * p.h + (h0 + row0)) * p.w + w0;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+          for (int c = 0; c < TW; ++c) {
+            const float z = affine((float)v[rr * TW + c], cc);
+            const long long off = (pix0 + (long long)rr * p.w + c) * p.cout + ch;
+            if (ch_ok) {
+              if constexpr (OUT_F32) ((float*)p.y)[off] = z;
+              else ((int8_t*)p.y)[off] = (int8_t)act_quant(z, e.qm);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 // TW in {32, 16, 8} selects the pixel-tile geometry {TH, TW, TN}: {8,32,1}, {16,16,1}, {8,8,4}.
 template <int KC, int STAGES, int TW, bool POOL, bool OUT_F32>
@@ -257,73 +345,179 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         umma_commit(tfull_bar(acc));                      // accumulator complete
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
-    const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
-    const int ch_in_tile = quarter * 32 + lane;
-    const Epi& e = p.epi;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile % p.m_tiles;
-      int pt = tile / p.m_tiles;
-      const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
-      const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
-      const int n0 = pt * TN, h0 = th_i * TH, w0 = tw_i * TW;
-      const int ch = mt * TILE_M + ch_in_tile;
-      const ChanConst cc = load_chan(e, ch, ch < p.cout);
-      const bool dec = decreasing(cc);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const int col0 = half * 128 + j * 64;
-        int v[64];
-        tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + col0), v);
-        tmem_ld_wait();
-        if (j == 1) {
-          // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        // 64 columns = rows [row0, row0 + 64/TW) of image n0 + img
-        const int img = col0 / (TH * TW);
-        const int row0 = (col0 % (TH * TW)) / TW;
-        const int nimg = n0 + img;
-        if (nimg >= p.n) continue;
-        if constexpr (POOL) {
-          constexpr int PR = 64 / TW / 2, PC = TW / 2;
-          const int oh_dim = p.h >> 1, ow_dim = p.w >> 1;
-          int8_t* ybase = (int8_t*)p.y + (((long long)nimg * oh_dim + ((h0 + row0) >> 1)) * ow_dim + (w0 >> 1)) * p.cout + ch;
+  } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
+    epilogue_role<TW, POOL, OUT_F32>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ------------------------------------------------------------------ K5: first layer (uint8 pixels, Cin = 3)
+// Same MMA / TMEM / epilogue machinery, but K = 27 (padded to 32) is too narrow for a TMA box (the channel
+// extent is 3 bytes), so four producer warps build the im2col B tile in shared memory themselves:
+// one 32-byte row per output pixel = the three 9-byte segments x[h-1..h+1][w-1..w+1][0..2] of the NHWC image.
+// Both operands use the un-swizzled K-major "interleaved" layout (8 rows x 16 B core matrices): the two
+// 16-byte K chunks of a row group are 128 B apart (LBO), row groups 256 B apart (SBO).  The packed kernel
+// ([Cout][9][4] int8 from K0) is re-laid-out once per CTA into the resident A tiles.  The activations are
+// UNSIGNED (pixel levels 0..255): b_format = u8, a_format = s8.  One tcgen05.mma per 256-pixel tile.
+constexpr int K5_PRODUCER_WARPS = 4;
+constexpr int K5_THREADS = 128 + NUM_EPI_WARPS * 32 + K5_PRODUCER_WARPS * 32;   // 512
+constexpr int K5_STAGES = 4;
+constexpr int K5_B_BYTES = TILE_N * 32;          // 8 KB per stage
+constexpr int K5_ROW_PITCH = 104;                // 4 B zero pad | 96 B row | 4 B zero pad
+constexpr int K5_HALO_BYTES = 10 * K5_ROW_PITCH;
+
+__device__ __forceinline__ uint64_t make_smem_desc_interleaved(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                                      // layout_type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct K5Smem {
+  static constexpr int A_OFFSET = 0;                                   // up to 2 m-tiles x 4 KB
+  static constexpr int B_OFFSET = 2 * TILE_M * 32;
+  static constexpr int HALO_OFFSET = B_OFFSET + K5_STAGES * K5_B_BYTES;
+  static constexpr int BAR_OFFSET = (HALO_OFFSET + 2 * K5_HALO_BYTES + 15) / 16 * 16;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <bool POOL, bool OUT_F32>
+__global__ void __launch_bounds__(K5_THREADS, 1)
+conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const TcParams p) {
+  constexpr int TW = 32, TH = 8;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + K5Smem::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (K5_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * K5_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * K5_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * K5_STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + K5Smem::BAR_OFFSET + 8 * (2 * K5_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // resident A tiles: row = output channel (zero rows beyond Cout), K byte 3*tap + c
+  for (int i = threadIdx.x; i < p.m_tiles * TILE_M * 2; i += K5_THREADS) {
+    const int j = i & 1;                 // which 16-byte K chunk
+    const int row = i >> 1;              // channel within the padded [m_tiles*128]
+    uint32_t wd[4] = {0, 0, 0, 0};
+    if (row < p.cout) {
 #pragma unroll
-          for (int pr = 0; pr < PR; ++pr) {
-#pragma unroll
-            for (int pc = 0; pc < PC; ++pc) {
-              const int i00 = (2 * pr) * TW + 2 * pc;
-              const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
-              const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
-              const float z = affine((float)(dec ? mn : mx), cc);
-              ybase[((long long)pr * ow_dim + pc) * p.cout] = (int8_t)act_quant(z, e.qm);
-            }
-          }
-        } else {
-          constexpr int R = 64 / TW;
-          const long long pix0 = ((long long)nimg * p.h + (h0 + row0)) * p.w + w0;
-#pragma unroll
-          for (int rr = 0; rr < R; ++rr) {
-#pragma unroll
-            for (int c = 0; c < TW; ++c) {
-              const float z = affine((float)v[rr * TW + c], cc);
-              const long long off = (pix0 + (long long)rr * p.w + c) * p.cout + ch;
-              if constexpr (OUT_F32) ((float*)p.y)[off] = z;
-              else ((int8_t*)p.y)[off] = (int8_t)act_quant(z, e.qm);
-            }
-          }
+      for (int b = 0; b < 16; ++b) {
+        const int k = j * 16 + b;
+        if (k < 27) {
+          const uint32_t v = (uint8_t)wpk[((long long)row * 9 + k / 3) * 4 + k % 3];
+          wd[b >> 2] |= v << (8 * (b & 3));
         }
       }
+    }
+    const int mt = row / TILE_M, r = row % TILE_M;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sg + K5Smem::A_OFFSET + mt * (TILE_M * 32) + (r >> 3) * 256 + j * 128 + (r & 7) * 16);
+    dst[0] = wd[0]; dst[1] = wd[1]; dst[2] = wd[2]; dst[3] = wd[3];
+  }
+  // zero the halo pads once (bytes 0..3 and 100..103 of every row, both buffers)
+  for (int i = threadIdx.x; i < 2 * 10 * 2; i += K5_THREADS) {
+    const int row = i >> 1, side = i & 1;
+    *reinterpret_cast<uint32_t*>(sg + K5Smem::HALO_OFFSET + row * K5_ROW_PITCH + (side ? 100 : 0)) = 0u;
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < K5_STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCER_WARPS * 32); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();                   // A tiles were written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, /*a signed*/ true, /*b unsigned*/ false);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int mt = tile % p.m_tiles;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc_interleaved(smem_base + K5Smem::A_OFFSET + mt * (TILE_M * 32), 128, 256);
+        const uint64_t b_desc = make_smem_desc_interleaved(smem_base + K5Smem::B_OFFSET + stage * K5_B_BYTES, 128, 256);
+        umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc, b_desc, idesc, 0u);
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == K5_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
+    epilogue_role<TW, POOL, OUT_F32>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane);
+  } else if (warp >= 4 + NUM_EPI_WARPS) {
+    // ===================== im2col producers (128 threads) =====================
+    const int t = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int pt = tile / p.m_tiles;
+      const int th_i = pt % p.tiles_h;
+      const int nimg = pt / p.tiles_h;
+      const int h0 = th_i * TH;
+      uint8_t* halo = sg + K5Smem::HALO_OFFSET + (it & 1) * K5_HALO_BYTES;
+      // rows h0-1 .. h0+8 of the image, 96 B each = 24 words; out-of-image rows are zero (SAME padding)
+      for (int i = t; i < 240; i += K5_PRODUCER_WARPS * 32) {
+        const int row = i / 24, wd = i % 24;
+        const int gh = h0 - 1 + row;
+        uint32_t v = 0;
+        if (gh >= 0 && gh < p.h)
+          v = __ldg(reinterpret_cast<const uint32_t*>(x + ((long long)nimg * p.h + gh) * (TW * 3)) + wd);
+        *reinterpret_cast<uint32_t*>(halo + row * K5_ROW_PITCH + 4 + wd * 4) = v;
+      }
+      named_bar_sync(1, K5_PRODUCER_WARPS * 32);
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* btile = sg + K5Smem::B_OFFSET + stage * K5_B_BYTES;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int pix = t + q * 128;                 // tile pixel = column of the accumulator
+        const int th = pix >> 5, tw = pix & 31;
+        uint32_t wd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const uint8_t* seg = halo + (th + r) * K5_ROW_PITCH + 1 + 3 * tw;     // pixel (w-1) starts at 4 + 3*(w-1)
+#pragma unroll
+          for (int b = 0; b < 9; ++b) {
+            const int k = 9 * r + b;
+            wd[k >> 2] |= (uint32_t)seg[b] << (8 * (k & 3));
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(btile + (pix >> 3) * 256 + (pix & 7) * 16);
+        dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        dst[8] = make_uint4(wd[4], wd[5], wd[6], wd[7]);                        // +128 B: second K chunk
+      }
+      fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(full_bar(stage));
+      if (++stage == K5_STAGES) { stage = 0; phase ^= 1u; }
     }
   }
 
@@ -386,13 +580,7 @@ int launch_kc(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, i
 
 }  // namespace
 
-bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
-  Geometry g;
-  if (d.in_kind != QNNB_KIND_I8) { *why = "input must be int8 levels"; return false; }
-  if (d.kh != 3 || d.kw != 3 || d.stride != 1) { *why = "only 3x3 stride 1"; return false; }
-  if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
-  if (d.cout % 128 != 0) { *why = "Cout must be a multiple of 128"; return false; }
-  if (!pick_geometry(d.h, d.w, &g)) { *why = "spatial size must be 32xH(H%8==0), 16x16k or 8x8"; return false; }
+static bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
   if (d.epi.res_kind != QNNB_KIND_NONE) { *why = "residual epilogue not on the tensor-core path"; return false; }
   if (d.epi.act == QNNB_ACT_QUANT) return true;
   if (d.epi.act == QNNB_ACT_NONE && d.epi.pool == 0) return true;
@@ -400,7 +588,53 @@ bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   return false;
 }
 
+static bool first_layer_shape(const qnnb_conv_desc& d) {
+  return d.in_kind == QNNB_KIND_U8 && d.cin == 3 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.w == 32 && d.h % 8 == 0 &&
+         d.cout <= 256;
+}
+
+bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
+  Geometry g;
+  if (first_layer_shape(d)) return epilogue_ok(d, why);
+  if (d.in_kind != QNNB_KIND_I8) { *why = "input must be int8 levels (or uint8 32-wide RGB for the first layer)"; return false; }
+  if (d.kh != 3 || d.kw != 3 || d.stride != 1) { *why = "only 3x3 stride 1"; return false; }
+  if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
+  if (d.cout % 128 != 0) { *why = "Cout must be a multiple of 128"; return false; }
+  if (!pick_geometry(d.h, d.w, &g)) { *why = "spatial size must be 32xH(H%8==0), 16x16k or 8x8"; return false; }
+  return epilogue_ok(d, why);
+}
+
+static int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
+  TcParams p;
+  p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
+  p.tiles_w = 1;
+  p.tiles_h = d.h / 8;
+  p.tiles_n = d.n;
+  p.m_tiles = ceil_div(d.cout, TILE_M);
+  p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
+  p.kchunks = 1;
+  p.y = y;
+  p.epi = make_epi(d.epi);
+  int dev = 0, sms = 0;
+  QNNB_CUDA(cudaGetDevice(&dev));
+  QNNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const bool pool = d.epi.pool == 2;
+  const bool f32 = d.epi.act == QNNB_ACT_NONE;
+  constexpr int smem = K5Smem::TOTAL;
+  auto go = [&](auto kern) -> int {
+    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, K5_THREADS, smem, st>>>((const uint8_t*)x, (const int8_t*)w, p);
+    QNNB_CUDA(cudaGetLastError());
+    return QNNB_OK;
+  };
+  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true>);
+  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false>);
+  return go(conv3x3_u8c3_tc_kernel<false, false>);
+}
+
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
+  if (first_layer_shape(d)) return launch_first_layer(d, x, w, y, st);
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
   Geometry g;

@@ -99,6 +99,68 @@ dense_kernel(const DenseP p) {
   }
 }
 
+// Fast path (int8 / bit-packed inputs, units <= 16, K a multiple of 16 bytes): the packed kernel is staged
+// once per CTA into shared memory and every lane streams 16-byte vectors of its image (512 B per warp
+// per step, fully coalesced), so HBM traffic is exactly one read of x.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+dense_smem_kernel(const DenseP p) {
+  extern __shared__ uint4 swv[];
+  const int kvec = p.kwords >> 2;
+  const uint4* wg = reinterpret_cast<const uint4*>(p.w);
+  for (int i = threadIdx.x; i < p.units * kvec; i += 256) swv[i] = __ldg(wg + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const bool active = lane < p.units;
+  const ChanConst cc = load_chan(p.epi, lane, active);
+  for (int img = blockIdx.x * 8 + warp; img < p.n; img += gridDim.x * 8) {
+    int acc[UG];
+#pragma unroll
+    for (int u = 0; u < UG; ++u) acc[u] = 0;
+    const uint4* xr = reinterpret_cast<const uint4*>(p.x) + (long long)img * kvec;
+    for (int kv = lane; kv < kvec; kv += 32) {
+      const uint4 xv = __ldg(xr + kv);
+#pragma unroll
+      for (int u = 0; u < UG; ++u) {
+        if (u < p.units) {
+          const uint4 wv = swv[u * kvec + kv];
+          if constexpr (KIND == QNNB_KIND_B1) {
+            acc[u] += __popc(xv.x ^ wv.x) + __popc(xv.y ^ wv.y) + __popc(xv.z ^ wv.z) + __popc(xv.w ^ wv.w);
+          } else {
+            acc[u] = __dp4a((int)xv.x, (int)wv.x, acc[u]);
+            acc[u] = __dp4a((int)xv.y, (int)wv.y, acc[u]);
+            acc[u] = __dp4a((int)xv.z, (int)wv.z, acc[u]);
+            acc[u] = __dp4a((int)xv.w, (int)wv.w, acc[u]);
+          }
+        }
+      }
+    }
+    float z = 0.f;
+#pragma unroll
+    for (int u = 0; u < UG; ++u) {
+      int v = acc[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if constexpr (KIND == QNNB_KIND_B1) v = p.fin - 2 * v;
+      if (lane == u) z = (float)v;
+    }
+    z = affine(z, cc);
+    if (p.softmax) {
+      if (active && p.logits) p.logits[(long long)img * p.units + lane] = z;
+      float m = active ? z : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float ex = active ? expf(z - m) : 0.f;
+      float sum = ex;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      z = ex / sum;
+    }
+    if (active) p.y[(long long)img * p.units + lane] = z;
+  }
+}
+
 }  // namespace
 
 int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st) {
@@ -112,8 +174,21 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
   p.x = x; p.w = w; p.y = y; p.logits = logits; p.softmax = d.softmax;
   p.epi = make_epi(d.epi);
   int blocks = ceil_div(d.n, 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
+  const size_t wbytes = (size_t)d.units * p.kwords * 4;
+  if (d.in_kind != QNNB_KIND_F32 && d.units <= UG && (p.kwords & 3) == 0 && wbytes <= 160 * 1024) {
+    int fb = blocks > 148 * 2 ? 148 * 2 : blocks;
+    if (d.in_kind == QNNB_KIND_I8) {
+      QNNB_CUDA(cudaFuncSetAttribute(dense_smem_kernel<QNNB_KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+      dense_smem_kernel<QNNB_KIND_I8><<<fb, 256, wbytes, st>>>(p);
+    } else {
+      QNNB_CUDA(cudaFuncSetAttribute(dense_smem_kernel<QNNB_KIND_B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+      dense_smem_kernel<QNNB_KIND_B1><<<fb, 256, wbytes, st>>>(p);
+    }
+    QNNB_CUDA(cudaGetLastError());
+    return QNNB_OK;
+  }
+  if (blocks > 148 * 8) blocks = 148 * 8;
   switch (d.in_kind) {
     case QNNB_KIND_I8: dense_kernel<QNNB_KIND_I8><<<blocks, 256, 0, st>>>(p); break;
     case QNNB_KIND_B1: dense_kernel<QNNB_KIND_B1><<<blocks, 256, 0, st>>>(p); break;

@@ -362,3 +362,48 @@ def test_conv2d_tcgen05_bit_exact(case):
     assert got.shape == want.shape
     bad = np.argwhere(got != want)
     assert bad.shape[0] == 0, "level mismatches: %d of %d, first %s" % (bad.shape[0], want.size, bad[:8].tolist())
+
+
+# --------------------------------------------------------------------------- tcgen05 first layer (K5: uint8 RGB, im2col producers)
+K5_CASES = [
+    # n, h, cout, nb, abits, pool, f32_out
+    (1, 32, 64, 4, 4, False, True),
+    (3, 32, 64, 4, 4, True, False),       # cfg3 layer 1
+    (2, 32, 256, 8, 8, False, False),     # cfg4 layer 1 (two channel tiles)
+    (2, 32, 16, 4, 4, False, False),      # ResNet stem width (mostly padding channels)
+    (3, 16, 128, 2, 2, True, False),      # non-square map, 32 wide
+    (150, 32, 64, 4, 4, True, False),     # 600 tiles: persistent loop
+]
+
+
+@pytest.mark.parametrize("case", K5_CASES, ids=["n%d_h%d_c%d_w%da%d%s%s" % (c[0], c[1], c[2], c[3], c[4], "_pool" if c[5] else "", "_f32" if c[6] else "") for c in K5_CASES])
+def test_first_layer_tcgen05_bit_exact(case):
+    q, L, K = _mods()
+    n, h, cout, nb, abits, pool, f32_out = case
+    rng = np.random.default_rng(_seed(("k5",) + case))
+    x = rng.integers(0, 256, size=(n, h, 32, 3), dtype=np.uint8)
+    x[0, 0, :4] = 255
+    x[0, -1, -4:] = 255
+    kernel = rng.uniform(-1, 1, size=(3, 3, 3, cout)).astype(F32)
+    wp = K.pack_weights(dev(kernel), L.W_QUANT, nb, 1.0, L.WFMT_I8)
+    xq = K.QTensor("u8", dev(x), 1.0 / 255.0, 3)
+    if f32_out:
+        epi = K.make_epilogue(1.0, act=L.ACT_NONE)
+        got = K.conv2d(xq, wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05).data.cpu().numpy()
+        want = exact.conv_accumulate(x.astype(np.int64), exact.quantize_levels(kernel, nb), 1).astype(F32)
+        bad = np.argwhere(got != want)
+        assert bad.shape[0] == 0, "accumulator mismatches: %d of %d, first %s got %s want %s" % (
+            bad.shape[0], want.size, bad[:6].tolist(), [got[tuple(b)] for b in bad[:6]], [want[tuple(b)] for b in bad[:6]])
+        return
+    bias = rng.uniform(-0.3, 0.3, size=cout).astype(F32)
+    bn = (rng.uniform(0.3, 0.9, cout).astype(F32) * rng.choice([1, 1, -1], cout).astype(F32),
+          rng.uniform(-0.2, 0.2, cout).astype(F32), (rng.uniform(-0.2, 0.2, cout) * np.sqrt(3.0)).astype(F32),
+          (rng.uniform(0.5, 1.5, cout) * 3.0).astype(F32))
+    want, _ = oracle_layer(x, "u8", 1.0 / 255.0, kernel, "quantized", nb, 1.0, 1, bias=bias, bn=bn, eps=1e-4, act="quant", abits=abits, pool=pool)
+    i_, s_ = K.bn_constants(*bn, 1e-4)
+    epi = K.make_epilogue(K.acc_scale(1.0 / 255.0, 1.0 / (1 << (nb - 1))), bias=dev(bias), bn_inv=dev(i_), bn_shift=dev(s_),
+                          act=L.ACT_QUANT, abits=abits, pool=2 if pool else 0)
+    got = K.conv2d(xq, wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05).data.cpu().numpy().astype(np.int32)
+    assert got.shape == want.shape
+    bad = np.argwhere(got != want)
+    assert bad.shape[0] == 0, "level mismatches: %d of %d, first %s" % (bad.shape[0], want.size, bad[:8].tolist())
