@@ -16,6 +16,11 @@
 // the 64B/128B swizzle the UMMA shared-memory descriptor expects.  The A tile is a 2-D box
 // {KC, 128} of the packed kernel [Cout][9*Cin].
 //
+// Output path: the epilogue threads write their int8 levels into a [pixel][128 channel] staging tile in
+// shared memory (byte stores, 32 consecutive bytes per warp instruction), then one thread issues a single
+// 4-D TMA store of the whole tile ({128, TW', TH', TN} box of the NHWC output; out-of-range images are
+// clipped by the TMA unit), so HBM sees full 128-byte rows.
+//
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..11 = epilogue (two warps per TMEM lane quarter, each takes half of the columns).
 // Pipelines: smem ring full/empty (TMA <-> MMA), 2 TMEM accumulators full/empty (MMA <-> epilogue),
@@ -79,6 +84,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
 }
@@ -136,7 +153,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// instruction descriptor: dense, S32 accumulate, A = B = signed int8, both K-major, N = 256, M = 128
+// Un-swizzled K-major "interleaved" layout: 8 rows x 16 B core matrices; consecutive 16-byte K chunks of a
+// row group are lbo bytes apart, 8-row groups sbo bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc_interleaved(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                                      // layout_type 0 = SWIZZLE_NONE
+}
+
+// instruction descriptor: dense, S32 accumulate, int8 operands (signedness per operand), both K-major
 __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed, bool b_signed) {
   return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -145,30 +173,32 @@ struct TcParams {
   int n, h, w, cin, cout;
   int tiles_w, tiles_h, tiles_n, m_tiles, num_tiles;
   int kchunks;            // cin / KC
+  int out_pitch;          // bytes per staged output row = channels per TMA-store box (<= 128)
   void* y;
   Epi epi;
 };
 
-template <int KC, int STAGES>
-struct SmemLayout {
-  static constexpr int A_BYTES = TILE_M * KC;
-  static constexpr int B_BYTES = TILE_N * KC;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+constexpr int EPI_BAR_ID = 2;
+constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
+
+template <bool POOL, bool OUT_F32>
+struct StageTile {
+  static constexpr int ROWS = OUT_F32 ? 0 : (POOL ? TILE_N / 4 : TILE_N);
+  static constexpr int BYTES = ROWS * TILE_M;
 };
 
 // ------------------------------------------------------------------ epilogue role (shared by K1 and K5)
 // Warp `warp` (4..11) drains TMEM lanes 32*(warp%4).. of both accumulators: thread = one output channel,
 // columns = the 256 pixels of the tile in {TN, TH, TW} order.  Fixed fp32 op order of common.cuh.
 template <int TW, bool POOL, bool OUT_F32>
-__device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                              int warp, int lane) {
+__device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
+                                              uint32_t tempty0, uint8_t* stg, int warp, int lane) {
   constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
   constexpr int TN = (TW == 8) ? 4 : 1;
   const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
   const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
   const int ch_in_tile = quarter * 32 + lane;
+  const bool leader = (warp == 4 && lane == 0);
   const Epi& e = p.epi;
   int it = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -184,77 +214,107 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
     const bool dec = decreasing(cc);
     const int acc = it & 1;
     const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+    if constexpr (!OUT_F32) {
+      // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
+      if (leader) tma_store_wait_read();
+      named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+    }
     mbar_wait(tfull0 + 8u * acc, acc_phase);
     tc_fence_after();
-    if (!warp_active) {
+    if (warp_active) {
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const int col0 = half * 128 + j * 64;
+        int v[64];
+        __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + col0), v);
+        tmem_ld_wait();
+        if (j == 1) {
+          // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        }
+        // 64 columns = rows [row0, row0 + 64/TW) of image n0 + img
+        const int img = col0 / (TH * TW);
+        const int row0 = (col0 % (TH * TW)) / TW;
+        if constexpr (OUT_F32) {
+          const int nimg = n0 + img;
+          if (nimg >= p.n) continue;               // warp-uniform (ragged last image group)
+          constexpr int R = 64 / TW;
+          const long long pix0 = ((long long)nimg * p.h + (h0 + row0)) * p.w + w0;
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+            for (int c = 0; c < TW; ++c) {
+              const float z = affine((float)v[rr * TW + c], cc);
+              if (ch_ok) ((float*)p.y)[(pix0 + (long long)rr * p.w + c) * p.cout + ch] = z;
+            }
+          }
+        } else if constexpr (POOL) {
+          constexpr int PR = 64 / TW / 2, PC = TW / 2;
+          uint8_t* srow = stg + (img * (TH / 2) * PC + (row0 >> 1) * PC) * p.out_pitch + ch_in_tile;
+#pragma unroll
+          for (int pr = 0; pr < PR; ++pr) {
+#pragma unroll
+            for (int pc = 0; pc < PC; ++pc) {
+              const int i00 = (2 * pr) * TW + 2 * pc;
+              const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
+              const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
+              const float z = affine((float)(dec ? mn : mx), cc);
+              if (ch_ok) srow[(pr * PC + pc) * p.out_pitch] = (uint8_t)act_quant(z, e.qm);
+            }
+          }
+        } else {
+          uint8_t* srow = stg + col0 * p.out_pitch + ch_in_tile;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float z = affine((float)v[c], cc);
+            if (ch_ok) srow[c * p.out_pitch] = (uint8_t)act_quant(z, e.qm);
+          }
+        }
+      }
+    } else {
       // this lane quarter holds only padding channels: nothing to read
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-      continue;
     }
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-      const int col0 = half * 128 + j * 64;
-      int v[64];
-      __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
-      tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + col0), v);
-      tmem_ld_wait();
-      if (j == 1) {
-        // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-      }
-      // 64 columns = rows [row0, row0 + 64/TW) of image n0 + img
-      const int img = col0 / (TH * TW);
-      const int row0 = (col0 % (TH * TW)) / TW;
-      const int nimg = n0 + img;
-      if (nimg >= p.n) continue;               // warp-uniform (ragged last image group)
-      if constexpr (POOL) {
-        constexpr int PR = 64 / TW / 2, PC = TW / 2;
-        const int oh_dim = p.h >> 1, ow_dim = p.w >> 1;
-        int8_t* ybase = (int8_t*)p.y + (((long long)nimg * oh_dim + ((h0 + row0) >> 1)) * ow_dim + (w0 >> 1)) * p.cout + ch;
-#pragma unroll
-        for (int pr = 0; pr < PR; ++pr) {
-#pragma unroll
-          for (int pc = 0; pc < PC; ++pc) {
-            const int i00 = (2 * pr) * TW + 2 * pc;
-            const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
-            const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
-            const float z = affine((float)(dec ? mn : mx), cc);
-            if (ch_ok) ybase[((long long)pr * ow_dim + pc) * p.cout] = (int8_t)act_quant(z, e.qm);
-          }
-        }
-      } else {
-        constexpr int R = 64 / TW;
-        const long long pix0 = ((long long)nimg * p.h + (h0 + row0)) * p.w + w0;
-#pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-#pragma unroll
-          for (int c = 0; c < TW; ++c) {
-            const float z = affine((float)v[rr * TW + c], cc);
-            const long long off = (pix0 + (long long)rr * p.w + c) * p.cout + ch;
-            if (ch_ok) {
-              if constexpr (OUT_F32) ((float*)p.y)[off] = z;
-              else ((int8_t*)p.y)[off] = (int8_t)act_quant(z, e.qm);
-            }
-          }
-        }
+    if constexpr (!OUT_F32) {
+      fence_proxy_async();                         // staging writes -> visible to the TMA (async proxy)
+      named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+      if (leader) {
+        if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, h0 >> 1, n0);
+        else tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0, h0, n0);
+        tma_store_commit();
       }
     }
   }
+  if constexpr (!OUT_F32) {
+    if (leader) tma_store_wait_all();
+  }
 }
 
-// ------------------------------------------------------------------ the kernel
+template <int KC, int STAGES, bool POOL, bool OUT_F32>
+struct SmemLayout {
+  static constexpr int A_BYTES = TILE_M * KC;
+  static constexpr int B_BYTES = TILE_N * KC;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + StageTile<POOL, OUT_F32>::BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+};
+
+// ------------------------------------------------------------------ K1: the int8 implicit-GEMM kernel
 // TW in {32, 16, 8} selects the pixel-tile geometry {TH, TW, TN}: {8,32,1}, {16,16,1}, {8,8,4}.
 template <int KC, int STAGES, int TW, bool POOL, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                     const __grid_constant__ CUtensorMap map_y, const TcParams p) {
   constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
   constexpr int TN = (TW == 8) ? 4 : 1;
   static_assert(TH * TW * TN == TILE_N, "tile geometry");
-  using SL = SmemLayout<KC, STAGES>;
+  using SL = SmemLayout<KC, STAGES, POOL, OUT_F32>;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024 B alignment
@@ -274,6 +334,7 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_y);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -346,7 +407,7 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<TW, POOL, OUT_F32>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane);
+    epilogue_role<TW, POOL, OUT_F32>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), smem_gen + SL::STG_OFFSET, warp, lane);
   }
 
   tc_fence_before();
@@ -357,87 +418,81 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   }
 }
 
-
 // ------------------------------------------------------------------ K5: first layer (uint8 pixels, Cin = 3)
-// Same MMA / TMEM / epilogue machinery, but K = 27 (padded to 32) is too narrow for a TMA box (the channel
-// extent is 3 bytes), so four producer warps build the im2col B tile in shared memory themselves:
-// one 32-byte row per output pixel = the three 9-byte segments x[h-1..h+1][w-1..w+1][0..2] of the NHWC image.
-// Both operands use the un-swizzled K-major "interleaved" layout (8 rows x 16 B core matrices): the two
-// 16-byte K chunks of a row group are 128 B apart (LBO), row groups 256 B apart (SBO).  The packed kernel
-// ([Cout][9][4] int8 from K0) is re-laid-out once per CTA into the resident A tiles.  The activations are
-// UNSIGNED (pixel levels 0..255): b_format = u8, a_format = s8.  One tcgen05.mma per 256-pixel tile.
+// Same MMA / TMEM / epilogue machinery, but the channel extent (3 bytes) is too narrow for a TMA box, so six
+// producer warps build the im2col B tile in shared memory themselves.  The RGB rows of the tile's halo
+// (10 image rows) are expanded to RGBX words while they are staged, so a pixel's 3x3 patch is nine aligned
+// 32-bit shared loads: K = 9 taps x 4 bytes = 36, padded to 64 (two tcgen05.mma per 256-pixel tile), which
+// is also exactly the [Cout][9][4] layout K0 packs the kernel in.  Both operands use the un-swizzled
+// K-major "interleaved" layout (8 rows x 16 B core matrices, 16-byte K chunks 128 B apart, row groups 512 B
+// apart).  The activations are UNSIGNED pixel levels: b_format = u8, a_format = s8.  Global loads of the
+// next tile's halo are issued before the current tile is built (software pipelining).
 constexpr int K5_PRODUCER_WARPS = 4;
-constexpr int K5_THREADS = 128 + NUM_EPI_WARPS * 32 + K5_PRODUCER_WARPS * 32;   // 512
+constexpr int K5_PRODUCERS = K5_PRODUCER_WARPS * 32;
+constexpr int K5_THREADS = 128 + NUM_EPI_WARPS * 32 + K5_PRODUCERS;   // 512
 constexpr int K5_STAGES = 4;
-constexpr int K5_B_BYTES = TILE_N * 32;          // 8 KB per stage
-constexpr int K5_ROW_PITCH = 104;                // 4 B zero pad | 96 B row | 4 B zero pad
+constexpr int K5_KB = 64;                          // K bytes per row (36 used)
+constexpr int K5_B_BYTES = TILE_N * K5_KB;         // 16 KB per stage
+constexpr int K5_ROW_PITCH = 160;                  // bytes per staged halo row: pixel p (-1..32) at byte 16 + 4*p
 constexpr int K5_HALO_BYTES = 10 * K5_ROW_PITCH;
 
-__device__ __forceinline__ uint64_t make_smem_desc_interleaved(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;                                      // layout_type 0 = SWIZZLE_NONE
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
+template <bool POOL, bool OUT_F32>
 struct K5Smem {
-  static constexpr int A_OFFSET = 0;                                   // up to 2 m-tiles x 4 KB
-  static constexpr int B_OFFSET = 2 * TILE_M * 32;
+  static constexpr int A_OFFSET = 0;                                   // up to 2 m-tiles x 8 KB
+  static constexpr int B_OFFSET = 2 * TILE_M * K5_KB;
   static constexpr int HALO_OFFSET = B_OFFSET + K5_STAGES * K5_B_BYTES;
-  static constexpr int BAR_OFFSET = (HALO_OFFSET + 2 * K5_HALO_BYTES + 15) / 16 * 16;
+  static constexpr int STG_OFFSET = (HALO_OFFSET + 2 * K5_HALO_BYTES + 1023) / 1024 * 1024;
+  static constexpr int BAR_OFFSET = STG_OFFSET + StageTile<POOL, OUT_F32>::BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
 template <bool POOL, bool OUT_F32>
 __global__ void __launch_bounds__(K5_THREADS, 1)
-conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const TcParams p) {
+conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const __grid_constant__ CUtensorMap map_y,
+                       const TcParams p) {
   constexpr int TW = 32, TH = 8;
+  using SL = K5Smem<POOL, OUT_F32>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sg = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + K5Smem::BAR_OFFSET;
+  const uint32_t bar_base = smem_base + SL::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (K5_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * K5_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * K5_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * K5_STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + K5Smem::BAR_OFFSET + 8 * (2 * K5_STAGES + 4));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + SL::BAR_OFFSET + 8 * (2 * K5_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // resident A tiles: row = output channel (zero rows beyond Cout), K byte 3*tap + c
-  for (int i = threadIdx.x; i < p.m_tiles * TILE_M * 2; i += K5_THREADS) {
-    const int j = i & 1;                 // which 16-byte K chunk
-    const int row = i >> 1;              // channel within the padded [m_tiles*128]
+  // resident A tiles: row = output channel (zero rows beyond Cout), 16-byte K chunk j holds packed words 4j..4j+3
+  for (int i = threadIdx.x; i < p.m_tiles * TILE_M * 4; i += K5_THREADS) {
+    const int j = i & 3;
+    const int row = i >> 2;
     uint32_t wd[4] = {0, 0, 0, 0};
     if (row < p.cout) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(wpk) + (long long)row * 9;
 #pragma unroll
-      for (int b = 0; b < 16; ++b) {
-        const int k = j * 16 + b;
-        if (k < 27) {
-          const uint32_t v = (uint8_t)wpk[((long long)row * 9 + k / 3) * 4 + k % 3];
-          wd[b >> 2] |= v << (8 * (b & 3));
-        }
-      }
+      for (int b = 0; b < 4; ++b)
+        if (4 * j + b < 9) wd[b] = __ldg(src + 4 * j + b);
     }
     const int mt = row / TILE_M, r = row % TILE_M;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sg + K5Smem::A_OFFSET + mt * (TILE_M * 32) + (r >> 3) * 256 + j * 128 + (r & 7) * 16);
-    dst[0] = wd[0]; dst[1] = wd[1]; dst[2] = wd[2]; dst[3] = wd[3];
+    *reinterpret_cast<uint4*>(sg + SL::A_OFFSET + mt * (TILE_M * K5_KB) + (r >> 3) * 512 + j * 128 + (r & 7) * 16) =
+        make_uint4(wd[0], wd[1], wd[2], wd[3]);
   }
-  // zero the halo pads once (bytes 0..3 and 100..103 of every row, both buffers)
+  // zero what the producers never write: the 4th K chunk of every B row, and halo pixels -1 and 32
+  for (int i = threadIdx.x; i < K5_STAGES * TILE_N; i += K5_THREADS) {
+    const int st = i / TILE_N, pix = i % TILE_N;
+    *reinterpret_cast<uint4*>(sg + SL::B_OFFSET + st * K5_B_BYTES + (pix >> 3) * 512 + 3 * 128 + (pix & 7) * 16) = make_uint4(0, 0, 0, 0);
+  }
   for (int i = threadIdx.x; i < 2 * 10 * 2; i += K5_THREADS) {
     const int row = i >> 1, side = i & 1;
-    *reinterpret_cast<uint32_t*>(sg + K5Smem::HALO_OFFSET + row * K5_ROW_PITCH + (side ? 100 : 0)) = 0u;
+    *reinterpret_cast<uint32_t*>(sg + SL::HALO_OFFSET + row * K5_ROW_PITCH + (side ? 16 + 4 * 32 : 12)) = 0u;
   }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < K5_STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCER_WARPS * 32); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < K5_STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCERS); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -445,7 +500,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  fence_proxy_async();                   // A tiles were written through the generic proxy
+  fence_proxy_async();                   // A tiles / zero fills were written through the generic proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -464,56 +519,69 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint64_t a_desc = make_smem_desc_interleaved(smem_base + K5Smem::A_OFFSET + mt * (TILE_M * 32), 128, 256);
-        const uint64_t b_desc = make_smem_desc_interleaved(smem_base + K5Smem::B_OFFSET + stage * K5_B_BYTES, 128, 256);
+        const uint64_t a_desc = make_smem_desc_interleaved(smem_base + SL::A_OFFSET + mt * (TILE_M * K5_KB), 128, 512);
+        const uint64_t b_desc = make_smem_desc_interleaved(smem_base + SL::B_OFFSET + stage * K5_B_BYTES, 128, 512);
+        // K step k covers chunks 2k, 2k+1: advance the start address by 256 B
         umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc, b_desc, idesc, 0u);
+        umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc + 16u, b_desc + 16u, idesc, 1u);
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
         if (++stage == K5_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<TW, POOL, OUT_F32>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane);
+    epilogue_role<TW, POOL, OUT_F32>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), sg + SL::STG_OFFSET, warp, lane);
   } else if (warp >= 4 + NUM_EPI_WARPS) {
     // ===================== im2col producers (128 threads) =====================
     const int t = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    // halo staging work item of this thread: image row `hrow` (0..9), pixel group `grp` (4 pixels = 3 words)
+    const bool loader = t < 80;
+    const int hrow = t >> 3, grp = t & 7;
+    uint32_t g0 = 0, g1 = 0, g2 = 0;
+    auto issue_loads = [&](int tile) {
+      if (!loader) return;
       int pt = tile / p.m_tiles;
       const int th_i = pt % p.tiles_h;
       const int nimg = pt / p.tiles_h;
-      const int h0 = th_i * TH;
-      uint8_t* halo = sg + K5Smem::HALO_OFFSET + (it & 1) * K5_HALO_BYTES;
-      // rows h0-1 .. h0+8 of the image, 96 B each = 24 words; out-of-image rows are zero (SAME padding)
-      for (int i = t; i < 240; i += K5_PRODUCER_WARPS * 32) {
-        const int row = i / 24, wd = i % 24;
-        const int gh = h0 - 1 + row;
-        uint32_t v = 0;
-        if (gh >= 0 && gh < p.h)
-          v = __ldg(reinterpret_cast<const uint32_t*>(x + ((long long)nimg * p.h + gh) * (TW * 3)) + wd);
-        *reinterpret_cast<uint32_t*>(halo + row * K5_ROW_PITCH + 4 + wd * 4) = v;
+      const int gh = th_i * TH - 1 + hrow;
+      g0 = g1 = g2 = 0;
+      if (gh >= 0 && gh < p.h) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((long long)nimg * p.h + gh) * (TW * 3)) + grp * 3;
+        g0 = __ldg(src); g1 = __ldg(src + 1); g2 = __ldg(src + 2);
       }
-      named_bar_sync(1, K5_PRODUCER_WARPS * 32);
+    };
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    if (blockIdx.x < p.num_tiles) issue_loads(blockIdx.x);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      uint8_t* halo = sg + SL::HALO_OFFSET + (it & 1) * K5_HALO_BYTES;
+      if (loader) {
+        // 12 RGB bytes -> 4 RGBX words
+        const uint32_t p0 = g0 & 0x00FFFFFFu;
+        const uint32_t p1 = (g0 >> 24) | ((g1 & 0x0000FFFFu) << 8);
+        const uint32_t p2 = (g1 >> 16) | ((g2 & 0x000000FFu) << 16);
+        const uint32_t p3 = g2 >> 8;
+        *reinterpret_cast<uint4*>(halo + hrow * K5_ROW_PITCH + 16 + grp * 16) = make_uint4(p0, p1, p2, p3);
+      }
+      named_bar_sync(1, K5_PRODUCERS);
+      if (tile + (int)gridDim.x < p.num_tiles) issue_loads(tile + gridDim.x);      // prefetch the next tile's rows
       mbar_wait(empty_bar(stage), phase ^ 1u);
-      uint8_t* btile = sg + K5Smem::B_OFFSET + stage * K5_B_BYTES;
+      uint8_t* btile = sg + SL::B_OFFSET + stage * K5_B_BYTES;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int pix = t + q * 128;                 // tile pixel = column of the accumulator
         const int th = pix >> 5, tw = pix & 31;
-        uint32_t wd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t k[12];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const uint8_t* seg = halo + (th + r) * K5_ROW_PITCH + 1 + 3 * tw;     // pixel (w-1) starts at 4 + 3*(w-1)
-#pragma unroll
-          for (int b = 0; b < 9; ++b) {
-            const int k = 9 * r + b;
-            wd[k >> 2] |= (uint32_t)seg[b] << (8 * (k & 3));
-          }
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(halo + (th + r) * K5_ROW_PITCH + 12) + tw;   // pixel tw-1
+          k[3 * r + 0] = hp[0]; k[3 * r + 1] = hp[1]; k[3 * r + 2] = hp[2];
         }
-        uint4* dst = reinterpret_cast<uint4*>(btile + (pix >> 3) * 256 + (pix & 7) * 16);
-        dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-        dst[8] = make_uint4(wd[4], wd[5], wd[6], wd[7]);                        // +128 B: second K chunk
+        k[9] = k[10] = k[11] = 0;
+        uint4* dst = reinterpret_cast<uint4*>(btile + (pix >> 3) * 512 + (pix & 7) * 16);
+        dst[0] = make_uint4(k[0], k[1], k[2], k[3]);
+        dst[8] = make_uint4(k[4], k[5], k[6], k[7]);
+        dst[16] = make_uint4(k[8], k[9], k[10], k[11]);
       }
       fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
       mbar_arrive(full_bar(stage));
@@ -545,6 +613,16 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
 struct Geometry { int tw, th, tn; };
 
 bool pick_geometry(int h, int w, Geometry* g) {
@@ -554,33 +632,48 @@ bool pick_geometry(int h, int w, Geometry* g) {
   return false;
 }
 
+// tensor map of the int8 NHWC output for the epilogue's TMA store (box = one staged tile)
+int make_output_map(EncodeTiledFn encode, CUtensorMap* my, void* y, int n, int oh, int ow, int cout, int pitch, const Geometry& g, bool pool) {
+  cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)cout, (cuuint64_t)ow * cout, (cuuint64_t)oh * ow * cout};
+  cuuint32_t box[4] = {(cuuint32_t)pitch, (cuuint32_t)(pool ? g.tw / 2 : g.tw), (cuuint32_t)(pool ? g.th / 2 : g.th), (cuuint32_t)g.tn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(my, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(output) failed with %d", (int)r); return QNNB_ECUDA; }
+  return QNNB_OK;
+}
+
 template <int KC, int STAGES, int TW, bool POOL, bool OUT_F32>
-int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int grid, cudaStream_t st) {
+int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, cudaStream_t st) {
   auto kern = conv3x3_i8_tc_kernel<KC, STAGES, TW, POOL, OUT_F32>;
-  constexpr int smem = SmemLayout<KC, STAGES>::TOTAL;
-  QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, NUM_THREADS, smem, st>>>(mw, mx, p);
+  constexpr int smem = SmemLayout<KC, STAGES, POOL, OUT_F32>::TOTAL;
+  static_assert(smem <= 232448, "shared memory budget");
+  static bool configured = false;                 // per template instantiation
+  if (!configured) {
+    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, smem, st>>>(mw, mx, my, p);
   QNNB_CUDA(cudaGetLastError());
   return QNNB_OK;
 }
 
 template <int KC, int STAGES, int TW>
-int launch_tw(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int grid, bool pool, bool f32, cudaStream_t st) {
-  if (f32) return launch_variant<KC, STAGES, TW, false, true>(mw, mx, p, grid, st);
-  if (pool) return launch_variant<KC, STAGES, TW, true, false>(mw, mx, p, grid, st);
-  return launch_variant<KC, STAGES, TW, false, false>(mw, mx, p, grid, st);
+int launch_tw(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, bool pool, bool f32, cudaStream_t st) {
+  if (f32) return launch_variant<KC, STAGES, TW, false, true>(mw, mx, my, p, grid, st);
+  if (pool) return launch_variant<KC, STAGES, TW, true, false>(mw, mx, my, p, grid, st);
+  return launch_variant<KC, STAGES, TW, false, false>(mw, mx, my, p, grid, st);
 }
 
 template <int KC, int STAGES>
-int launch_kc(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int grid, int tw, bool pool, bool f32, cudaStream_t st) {
-  if (tw == 32) return launch_tw<KC, STAGES, 32>(mw, mx, p, grid, pool, f32, st);
-  if (tw == 16) return launch_tw<KC, STAGES, 16>(mw, mx, p, grid, pool, f32, st);
-  return launch_tw<KC, STAGES, 8>(mw, mx, p, grid, pool, f32, st);
+int launch_kc(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, int tw, bool pool, bool f32, cudaStream_t st) {
+  if (tw == 32) return launch_tw<KC, STAGES, 32>(mw, mx, my, p, grid, pool, f32, st);
+  if (tw == 16) return launch_tw<KC, STAGES, 16>(mw, mx, my, p, grid, pool, f32, st);
+  return launch_tw<KC, STAGES, 8>(mw, mx, my, p, grid, pool, f32, st);
 }
 
-}  // namespace
-
-static bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
+bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
   if (d.epi.res_kind != QNNB_KIND_NONE) { *why = "residual epilogue not on the tensor-core path"; return false; }
   if (d.epi.act == QNNB_ACT_QUANT) return true;
   if (d.epi.act == QNNB_ACT_NONE && d.epi.pool == 0) return true;
@@ -588,10 +681,47 @@ static bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
   return false;
 }
 
-static bool first_layer_shape(const qnnb_conv_desc& d) {
+bool first_layer_shape(const qnnb_conv_desc& d) {
   return d.in_kind == QNNB_KIND_U8 && d.cin == 3 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.w == 32 && d.h % 8 == 0 &&
-         d.cout <= 256;
+         d.cout <= 256 && d.cout % 16 == 0;
 }
+
+int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
+  TcParams p;
+  p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
+  p.tiles_w = 1;
+  p.tiles_h = d.h / 8;
+  p.tiles_n = d.n;
+  p.m_tiles = ceil_div(d.cout, TILE_M);
+  p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
+  p.kchunks = 1;
+  p.out_pitch = d.cout < TILE_M ? d.cout : TILE_M;
+  p.y = y;
+  p.epi = make_epi(d.epi);
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const bool pool = d.epi.pool == 2;
+  const bool f32 = d.epi.act == QNNB_ACT_NONE;
+  CUtensorMap my;
+  memset(&my, 0, sizeof(my));
+  if (!f32) {
+    Geometry g = {32, 8, 1};
+    int rc = make_output_map(encode, &my, y, d.n, pool ? d.h / 2 : d.h, pool ? d.w / 2 : d.w, d.cout, p.out_pitch, g, pool);
+    if (rc) return rc;
+  }
+  auto go = [&](auto kern, int smem) -> int {
+    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, K5_THREADS, smem, st>>>((const uint8_t*)x, (const int8_t*)w, my, p);
+    QNNB_CUDA(cudaGetLastError());
+    return QNNB_OK;
+  };
+  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true>, K5Smem<false, true>::TOTAL);
+  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false>, K5Smem<true, false>::TOTAL);
+  return go(conv3x3_u8c3_tc_kernel<false, false>, K5Smem<false, false>::TOTAL);
+}
+
+}  // namespace
 
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   Geometry g;
@@ -604,35 +734,6 @@ bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   return epilogue_ok(d, why);
 }
 
-static int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
-  TcParams p;
-  p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
-  p.tiles_w = 1;
-  p.tiles_h = d.h / 8;
-  p.tiles_n = d.n;
-  p.m_tiles = ceil_div(d.cout, TILE_M);
-  p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
-  p.kchunks = 1;
-  p.y = y;
-  p.epi = make_epi(d.epi);
-  int dev = 0, sms = 0;
-  QNNB_CUDA(cudaGetDevice(&dev));
-  QNNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  const bool pool = d.epi.pool == 2;
-  const bool f32 = d.epi.act == QNNB_ACT_NONE;
-  constexpr int smem = K5Smem::TOTAL;
-  auto go = [&](auto kern) -> int {
-    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, K5_THREADS, smem, st>>>((const uint8_t*)x, (const int8_t*)w, p);
-    QNNB_CUDA(cudaGetLastError());
-    return QNNB_OK;
-  };
-  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true>);
-  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false>);
-  return go(conv3x3_u8c3_tc_kernel<false, false>);
-}
-
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
   if (first_layer_shape(d)) return launch_first_layer(d, x, w, y, st);
   EncodeTiledFn encode = get_encode();
@@ -641,8 +742,11 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   pick_geometry(d.h, d.w, &g);
   const int KC = (d.cin % 128 == 0) ? 128 : 64;
   const CUtensorMapSwizzle swz = (KC == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const bool pool = d.epi.pool == 2;
+  const bool f32 = d.epi.act == QNNB_ACT_NONE;
 
-  CUtensorMap mw, mx;
+  CUtensorMap mw, mx, my;
+  memset(&my, 0, sizeof(my));
   {
     cuuint64_t dims[2] = {(cuuint64_t)9 * d.cin, (cuuint64_t)d.cout};
     cuuint64_t strides[1] = {(cuuint64_t)9 * d.cin};
@@ -661,6 +765,10 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(activations) failed with %d", (int)r); return QNNB_ECUDA; }
   }
+  if (!f32) {
+    int rc = make_output_map(encode, &my, y, d.n, pool ? d.h / 2 : d.h, pool ? d.w / 2 : d.w, d.cout, TILE_M, g, pool);
+    if (rc) return rc;
+  }
 
   TcParams p;
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
@@ -670,17 +778,13 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   p.m_tiles = d.cout / TILE_M;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.m_tiles;
   p.kchunks = d.cin / KC;
+  p.out_pitch = TILE_M;
   p.y = y;
   p.epi = make_epi(d.epi);
 
-  int dev = 0, sms = 0;
-  QNNB_CUDA(cudaGetDevice(&dev));
-  QNNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  const bool pool = d.epi.pool == 2;
-  const bool f32 = d.epi.act == QNNB_ACT_NONE;
-  if (KC == 128) return launch_kc<128, 4>(mw, mx, p, grid, g.tw, pool, f32, st);
-  return launch_kc<64, 6>(mw, mx, p, grid, g.tw, pool, f32, st);
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (KC == 128) return launch_kc<128, 4>(mw, mx, my, p, grid, g.tw, pool, f32, st);
+  return launch_kc<64, 6>(mw, mx, my, p, grid, g.tw, pool, f32, st);
 }
 
 }  // namespace qnnb
