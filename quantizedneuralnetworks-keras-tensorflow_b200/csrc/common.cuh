@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <math.h>
 
 #include "../../include/qnnb200.h"
 
@@ -73,6 +74,13 @@ static inline Epi make_epi(const qnnb_epilogue& e) {
 
 int validate_epilogue(const qnnb_epilogue& e, bool allow_pool, bool allow_residual);
 
+// true when x is a finite power of two whose folded constants stay far from the subnormal range
+static inline bool is_pow2_scale(float x) {
+  int ex;
+  float m = frexpf(x, &ex);
+  return x > 0.f && m == 0.5f && ex > -40 && ex < 40;
+}
+
 #ifdef __CUDACC__
 // Per-channel constants of the affine part (steps 1-3 of the fixed order).
 struct ChanConst {
@@ -115,6 +123,47 @@ __device__ __forceinline__ int act_quant(float z, float qm) {
 
 // binary_tanh(z) == +1  <=>  z > 2^-24   
 __device__ __forceinline__ bool act_sign(float z) { return z > 5.9604644775390625e-08f; }
+
+// ---- pre-scaled form of the same pipeline for the tensor-core epilogues ---------------------------------
+// q = clamp(rint(z * qm)) with z = ((f*s + bias)*inv + shift).  qm is a power of two, so it folds into inv and
+// shift without changing any rounding (scaling by 2^k commutes with round-to-nearest as long as nothing is
+// subnormal); when s is a power of two as well (int8 x int8 layers) it folds too:
+//   FOLD : zq = ((f + bias/s) * (inv*s*qm)) + shift*qm          general: zq = ((f*s + bias) * (inv*qm)) + shift*qm
+// Absent bias / BN are the neutral constants 0 / 1 / 0 (adding 0 and multiplying by a power of two are exact).
+struct QConst { float s, a, b, c; };
+
+template <bool FOLD>
+__device__ __forceinline__ QConst make_qconst(const Epi& e, int ch, bool valid) {
+  const float bias = (e.bias != nullptr && valid) ? __ldg(e.bias + ch) : 0.f;
+  const float inv = (e.bn_inv != nullptr && valid) ? __ldg(e.bn_inv + ch) : 1.f;
+  const float shift = (e.bn_inv != nullptr && valid) ? __ldg(e.bn_shift + ch) : 0.f;
+  QConst q;
+  if (FOLD) {
+    q.s = 1.f;
+    q.a = __fmul_rn(bias, __frcp_rn(e.acc_scale));
+    q.b = __fmul_rn(__fmul_rn(inv, e.acc_scale), e.qm);
+  } else {
+    q.s = e.acc_scale;
+    q.a = bias;
+    q.b = __fmul_rn(inv, e.qm);
+  }
+  q.c = __fmul_rn(shift, e.qm);
+  return q;
+}
+
+template <bool FOLD>
+__device__ __forceinline__ float qaffine(int acc, const QConst& q) {
+  float f = (float)acc;                         // cvt.rn
+  if (!FOLD) f = __fmul_rn(f, q.s);
+  f = __fadd_rn(f, q.a);
+  f = __fmul_rn(f, q.b);
+  return __fadd_rn(f, q.c);                     // == z * qm
+}
+
+// clamp bounds are integers, so clamping before the round-to-nearest-even conversion is identical to after
+__device__ __forceinline__ int quant_scaled(float zq, float qm) {
+  return __float2int_rn(fminf(fmaxf(zq, -qm), qm - 1.f));
+}
 
 __device__ __forceinline__ float act_leaky(float z, float alpha) { return z > 0.f ? z : __fmul_rn(alpha, z); }
 #endif  // __CUDACC__

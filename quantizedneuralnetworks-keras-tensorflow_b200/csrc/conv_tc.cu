@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -190,7 +190,8 @@ struct StageTile {
 // ------------------------------------------------------------------ epilogue role (shared by K1 and K5)
 // Warp `warp` (4..11) drains TMEM lanes 32*(warp%4).. of both accumulators: thread = one output channel,
 // columns = the 256 pixels of the tile in {TN, TH, TW} order.  Fixed fp32 op order of common.cuh.
-template <int TW, bool POOL, bool OUT_F32>
+// FOLD: acc_scale is a power of two (see QConst); PITCH: bytes per staged row (0 = runtime p.out_pitch).
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, uint8_t* stg, int warp, int lane) {
   constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
@@ -210,8 +211,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
     const int ch = mt * TILE_M + ch_in_tile;
     const bool ch_ok = ch < p.cout;
     const bool warp_active = (mt * TILE_M + quarter * 32) < p.cout;      // warp-uniform
-    const ChanConst cc = load_chan(e, ch, ch_ok);
-    const bool dec = decreasing(cc);
+    const ChanConst cc = load_chan(e, ch, ch_ok);                 // fp32 output path
+    const QConst qc = make_qconst<FOLD>(e, ch, ch_ok);            // quantised output path
+    const bool dec = qc.b < 0.f;
+    const int pitch = PITCH ? PITCH : p.out_pitch;
+    const float qm = e.qm;
     const int acc = it & 1;
     const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
     if constexpr (!OUT_F32) {
@@ -253,7 +257,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
           }
         } else if constexpr (POOL) {
           constexpr int PR = 64 / TW / 2, PC = TW / 2;
-          uint8_t* srow = stg + (img * (TH / 2) * PC + (row0 >> 1) * PC) * p.out_pitch + ch_in_tile;
+          // every lane of an active warp owns a real channel (Cout % 32 == 0 on this path)
+          uint8_t* srow = stg + (img * (TH / 2) * PC + (row0 >> 1) * PC) * pitch + ch_in_tile;
 #pragma unroll
           for (int pr = 0; pr < PR; ++pr) {
 #pragma unroll
@@ -261,17 +266,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
               const int i00 = (2 * pr) * TW + 2 * pc;
               const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
               const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
-              const float z = affine((float)(dec ? mn : mx), cc);
-              if (ch_ok) srow[(pr * PC + pc) * p.out_pitch] = (uint8_t)act_quant(z, e.qm);
+              srow[(pr * PC + pc) * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(dec ? mn : mx, qc), qm);
             }
           }
         } else {
-          uint8_t* srow = stg + col0 * p.out_pitch + ch_in_tile;
+          uint8_t* srow = stg + col0 * pitch + ch_in_tile;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float z = affine((float)v[c], cc);
-            if (ch_ok) srow[c * p.out_pitch] = (uint8_t)act_quant(z, e.qm);
-          }
+          for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
         }
       }
     } else {
@@ -407,7 +408,8 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<TW, POOL, OUT_F32>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), smem_gen + SL::STG_OFFSET, warp, lane);
+    epilogue_role<TW, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
+                                                                        smem_gen + SL::STG_OFFSET, warp, lane);
   }
 
   tc_fence_before();
@@ -446,7 +448,7 @@ struct K5Smem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <bool POOL, bool OUT_F32>
+template <bool POOL, bool OUT_F32, int PITCH>
 __global__ void __launch_bounds__(K5_THREADS, 1)
 conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const __grid_constant__ CUtensorMap map_y,
                        const TcParams p) {
@@ -530,7 +532,8 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<TW, POOL, OUT_F32>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), sg + SL::STG_OFFSET, warp, lane);
+    epilogue_role<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), sg + SL::STG_OFFSET,
+                                                            warp, lane);
   } else if (warp >= 4 + NUM_EPI_WARPS) {
     // ===================== im2col producers (128 threads) =====================
     const int t = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
@@ -683,7 +686,7 @@ bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
 
 bool first_layer_shape(const qnnb_conv_desc& d) {
   return d.in_kind == QNNB_KIND_U8 && d.cin == 3 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.w == 32 && d.h % 8 == 0 &&
-         d.cout <= 256 && d.cout % 16 == 0;
+         d.cout <= 256 && d.cout % 32 == 0;
 }
 
 int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
@@ -716,9 +719,17 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
     QNNB_CUDA(cudaGetLastError());
     return QNNB_OK;
   };
-  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true>, K5Smem<false, true>::TOTAL);
-  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false>, K5Smem<true, false>::TOTAL);
-  return go(conv3x3_u8c3_tc_kernel<false, false>, K5Smem<false, false>::TOTAL);
+  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true, 0>, K5Smem<false, true>::TOTAL);
+  if (p.out_pitch == 128) {
+    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 128>, K5Smem<true, false>::TOTAL);
+    return go(conv3x3_u8c3_tc_kernel<false, false, 128>, K5Smem<false, false>::TOTAL);
+  }
+  if (p.out_pitch == 64) {
+    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64>, K5Smem<true, false>::TOTAL);
+    return go(conv3x3_u8c3_tc_kernel<false, false, 64>, K5Smem<false, false>::TOTAL);
+  }
+  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 0>, K5Smem<true, false>::TOTAL);
+  return go(conv3x3_u8c3_tc_kernel<false, false, 0>, K5Smem<false, false>::TOTAL);
 }
 
 }  // namespace
@@ -731,6 +742,7 @@ bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
   if (d.cout % 128 != 0) { *why = "Cout must be a multiple of 128"; return false; }
   if (!pick_geometry(d.h, d.w, &g)) { *why = "spatial size must be 32xH(H%8==0), 16x16k or 8x8"; return false; }
+  if (d.epi.act == QNNB_ACT_QUANT && !is_pow2_scale(d.epi.acc_scale)) { *why = "acc_scale must be a power of two"; return false; }
   return epilogue_ok(d, why);
 }
 

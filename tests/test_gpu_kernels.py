@@ -370,7 +370,7 @@ K5_CASES = [
     (1, 32, 64, 4, 4, False, True),
     (3, 32, 64, 4, 4, True, False),       # cfg3 layer 1
     (2, 32, 256, 8, 8, False, False),     # cfg4 layer 1 (two channel tiles)
-    (2, 32, 16, 4, 4, False, False),      # ResNet stem width (mostly padding channels)
+    (2, 32, 32, 4, 4, False, False),      # narrow layer: one active lane quarter, runtime row pitch
     (3, 16, 128, 2, 2, True, False),      # non-square map, 32 wide
     (150, 32, 64, 4, 4, True, False),     # 600 tiles: persistent loop
 ]
