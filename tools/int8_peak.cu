@@ -1,0 +1,119 @@
+// Micro-benchmark: dense int8 tensor-core ceiling of this GPU for the exact instruction the conv kernels
+// issue (tcgen05.mma.cta_group::1.kind::i8, M=128, N=256, K=32, operands resident in shared memory with the
+// 128B swizzle, int32 accumulators in TMEM).  One CTA per SM, one thread issues back-to-back MMAs on random
+// operand bytes (data-dependent power), no loads, no epilogue.  Prints a JSON line; bench.py uses
+// profiles/int8_peak.json as the roofline denominator for the tensor-bound layers.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(128, 1) peak_kernel(int groups, uint32_t seed) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  uint8_t* gen = raw + (base - smem_u32(raw));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  // A: 128 x 128 B, B: 256 x 128 B, two copies each (ping-pong like a real pipeline)
+  const int total = 2 * (128 + 256) * 128;
+  uint32_t s = seed ^ (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
+  for (int i = threadIdx.x * 4; i < total; i += 128 * 4) {
+    s = s * 1664525u + 1013904223u;
+    *reinterpret_cast<uint32_t*>(gen + i) = s;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tslot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t phase = 0;
+    for (int g = 0; g < groups; ++g) {
+      // one "k-step" group = 16 MMAs (K = 512) into alternating accumulators
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t buf = (i >> 2) & 1;
+        const uint64_t a = desc_sw128(base + buf * (128 * 128)) + (uint64_t)((i & 3) * 2);
+        const uint64_t b = desc_sw128(base + 2 * 128 * 128 + buf * (256 * 128)) + (uint64_t)((i & 3) * 2);
+        const uint32_t d = tmem + ((g & 1) ? 256u : 0u);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"((uint32_t)(i > 0))
+            : "memory");
+      }
+      if ((g & 7) == 7 || g == groups - 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
+        }
+        phase ^= 1u;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+int main(int argc, char** argv) {
+  int groups = argc > 1 ? atoi(argv[1]) : 4000;
+  int reps = argc > 2 ? atoi(argv[2]) : 20;
+  int dev = 0, sms = 0, clk = 0;
+  cudaSetDevice(dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
+  const int smem = 2 * (128 + 256) * 128 + 1024;
+  cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  peak_kernel<<<sms, 128, smem>>>(groups, 1u);
+  if (cudaDeviceSynchronize() != cudaSuccess) { printf("{\"error\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+  double best = 1e30, total = 0;
+  // burst: best single launch; sustained: back-to-back launches
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0);
+    peak_kernel<<<sms, 128, smem>>>(groups, 2u + r);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventRecord(e0);
+  for (int r = 0; r < reps * 10; ++r) peak_kernel<<<sms, 128, smem>>>(groups, 100u + r);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms_all; cudaEventElapsedTime(&ms_all, e0, e1);
+  total = ms_all / (reps * 10);
+  const double ops = (double)sms * groups * 16.0 * 2.0 * 128 * 256 * 32;
+  printf("{\"int8_tops\": %.1f, \"int8_tops_sustained\": %.1f, \"sms\": %d, \"kernel_ms_best\": %.4f, \"kernel_ms_sustained\": %.4f, "
+         "\"how\": \"tcgen05.mma.cta_group::1.kind::i8 M=128 N=256 K=32 from swizzled smem, random operand bytes, %d MMAs per SM per launch; burst = best of %d launches, sustained = %d back-to-back launches\"}\n",
+         ops / (best * 1e-3) / 1e12, ops / (total * 1e-3) / 1e12, sms, best, total, groups * 16, reps, reps * 10);
+  return 0;
+}
