@@ -191,14 +191,19 @@ struct StageTile {
 // Warp `warp` (4..11) drains TMEM lanes 32*(warp%4).. of both accumulators: thread = one output channel,
 // columns = the 256 pixels of the tile in {TN, TH, TW} order.  Fixed fp32 op order of common.cuh.
 // FOLD: acc_scale is a power of two (see QConst); PITCH: bytes per staged row (0 = runtime p.out_pitch).
-template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH>
+// GROUPS (K5 only, TW = 32): when Cout <= 64 the 128 TMEM lanes hold GROUPS = 2 pixel groups of 64 channels --
+// lane L is channel L % 64 of the pixels 8*(L / 64) rows further down, so one tile covers 16 image rows.
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, uint8_t* stg, int warp, int lane) {
   constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
   constexpr int TN = (TW == 8) ? 4 : 1;
+  static_assert(GROUPS == 1 || TW == 32, "pixel groups only exist for the first-layer geometry");
   const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
   const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
-  const int ch_in_tile = quarter * 32 + lane;
+  const int group = (GROUPS == 2) ? (quarter >> 1) : 0;
+  const int grow = group * TH;                  // row offset of this lane's pixel group inside the tile
+  const int ch_in_tile = (GROUPS == 2) ? ((quarter & 1) * 32 + lane) : (quarter * 32 + lane);
   const bool leader = (warp == 4 && lane == 0);
   const Epi& e = p.epi;
   int it = 0;
@@ -207,10 +212,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
     int pt = tile / p.m_tiles;
     const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
     const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
-    const int n0 = pt * TN, h0 = th_i * TH, w0 = tw_i * TW;
+    const int n0 = pt * TN, h0 = th_i * (TH * GROUPS), w0 = tw_i * TW;
     const int ch = mt * TILE_M + ch_in_tile;
     const bool ch_ok = ch < p.cout;
-    const bool warp_active = (mt * TILE_M + quarter * 32) < p.cout;      // warp-uniform
+    const bool warp_active = (mt * TILE_M + ch_in_tile - lane) < p.cout; // warp-uniform
     const ChanConst cc = load_chan(e, ch, ch_ok);                 // fp32 output path
     const QConst qc = make_qconst<FOLD>(e, ch, ch_ok);            // quantised output path
     const bool dec = qc.b < 0.f;
@@ -246,7 +251,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
           const int nimg = n0 + img;
           if (nimg >= p.n) continue;               // warp-uniform (ragged last image group)
           constexpr int R = 64 / TW;
-          const long long pix0 = ((long long)nimg * p.h + (h0 + row0)) * p.w + w0;
+          const long long pix0 = ((long long)nimg * p.h + (h0 + grow + row0)) * p.w + w0;
 #pragma unroll
           for (int rr = 0; rr < R; ++rr) {
 #pragma unroll
@@ -258,7 +263,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         } else if constexpr (POOL) {
           constexpr int PR = 64 / TW / 2, PC = TW / 2;
           // every lane of an active warp owns a real channel (Cout % 32 == 0 on this path)
-          uint8_t* srow = stg + (img * (TH / 2) * PC + (row0 >> 1) * PC) * pitch + ch_in_tile;
+          uint8_t* srow = stg + (img * (TH / 2) * PC + ((grow + row0) >> 1) * PC) * pitch + ch_in_tile;
 #pragma unroll
           for (int pr = 0; pr < PR; ++pr) {
 #pragma unroll
@@ -270,7 +275,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             }
           }
         } else {
-          uint8_t* srow = stg + col0 * pitch + ch_in_tile;
+          uint8_t* srow = stg + (grow * TW + col0) * pitch + ch_in_tile;
 #pragma unroll
           for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
         }
@@ -421,80 +426,99 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 }
 
 // ------------------------------------------------------------------ K5: first layer (uint8 pixels, Cin = 3)
-// Same MMA / TMEM / epilogue machinery, but the channel extent (3 bytes) is too narrow for a TMA box, so six
-// producer warps build the im2col B tile in shared memory themselves.  The RGB rows of the tile's halo
-// (10 image rows) are expanded to RGBX words while they are staged, so a pixel's 3x3 patch is nine aligned
-// 32-bit shared loads: K = 9 taps x 4 bytes = 36, padded to 64 (two tcgen05.mma per 256-pixel tile), which
-// is also exactly the [Cout][9][4] layout K0 packs the kernel in.  Both operands use the un-swizzled
-// K-major "interleaved" layout (8 rows x 16 B core matrices, 16-byte K chunks 128 B apart, row groups 512 B
-// apart).  The activations are UNSIGNED pixel levels: b_format = u8, a_format = s8.  Global loads of the
-// next tile's halo are issued before the current tile is built (software pipelining).
+// Same MMA / TMEM / epilogue machinery, but the channel extent (3 bytes) is too narrow for a TMA box, so four
+// producer warps build the im2col B tile in shared memory themselves.  The RGB rows of the tile's halo are
+// expanded to RGBX words while they are staged, so a pixel's 3x3 patch is nine aligned 32-bit shared loads:
+// K = 9 taps x 4 bytes = 36, padded to 64, which is also exactly the [Cout][9][4] layout K0 packs the kernel in.
+// Both operands use the un-swizzled K-major "interleaved" layout (8 rows x 16 B core matrices, 16-byte K chunks
+// 128 B apart).  The activations are UNSIGNED pixel levels: b_format = u8, a_format = s8.  Global loads of the
+// next tile's halo rows are issued before the current tile is built (software pipelining).
+//
+// G pixel groups: with Cout <= 64 a 128-lane accumulator would be half empty, so G = 2 row blocks of 8 image
+// rows share one tile: B row n = [im2col(pixel n of block 0) | im2col(pixel n of block 1)] (K = 128) and the A
+// tile is block-diagonal (rows 0..63 = W in K bytes 0..63, rows 64..127 = W in K bytes 64..127), which makes
+// D[64 g + c][n] = conv(channel c, pixel n of block g): all 128 lanes and all 8 epilogue warps do useful work.
 constexpr int K5_PRODUCER_WARPS = 4;
 constexpr int K5_PRODUCERS = K5_PRODUCER_WARPS * 32;
 constexpr int K5_THREADS = 128 + NUM_EPI_WARPS * 32 + K5_PRODUCERS;   // 512
-constexpr int K5_STAGES = 4;
-constexpr int K5_KB = 64;                          // K bytes per row (36 used)
-constexpr int K5_B_BYTES = TILE_N * K5_KB;         // 16 KB per stage
+constexpr int K5_KB = 64;                          // K bytes per pixel group (36 used)
 constexpr int K5_ROW_PITCH = 160;                  // bytes per staged halo row: pixel p (-1..32) at byte 16 + 4*p
-constexpr int K5_HALO_BYTES = 10 * K5_ROW_PITCH;
 
-template <bool POOL, bool OUT_F32>
+template <bool POOL, bool OUT_F32, int G>
 struct K5Smem {
-  static constexpr int A_OFFSET = 0;                                   // up to 2 m-tiles x 8 KB
-  static constexpr int B_OFFSET = 2 * TILE_M * K5_KB;
-  static constexpr int HALO_OFFSET = B_OFFSET + K5_STAGES * K5_B_BYTES;
-  static constexpr int STG_OFFSET = (HALO_OFFSET + 2 * K5_HALO_BYTES + 1023) / 1024 * 1024;
-  static constexpr int BAR_OFFSET = STG_OFFSET + StageTile<POOL, OUT_F32>::BYTES;
+  static constexpr int STAGES = (G == 2) ? 3 : 4;
+  static constexpr int A_BYTES = 2 * TILE_M * K5_KB * G;                 // up to 2 m-tiles (G = 1) or one block-diagonal tile
+  static constexpr int B_BYTES = TILE_N * K5_KB * G;                     // per stage
+  static constexpr int HALO_ROWS = 8 * G + 2;
+  static constexpr int HALO_BYTES = HALO_ROWS * K5_ROW_PITCH;
+  static constexpr int A_OFFSET = 0;
+  static constexpr int B_OFFSET = A_BYTES;
+  static constexpr int HALO_OFFSET = B_OFFSET + STAGES * B_BYTES;
+  static constexpr int STG_OFFSET = (HALO_OFFSET + 2 * HALO_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STG_BYTES = OUT_F32 ? 0 : (POOL ? TILE_N * G / 4 : TILE_N * G) * (TILE_M / G);
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <bool POOL, bool OUT_F32, int PITCH>
+template <bool POOL, bool OUT_F32, int PITCH, int G>
 __global__ void __launch_bounds__(K5_THREADS, 1)
 conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const __grid_constant__ CUtensorMap map_y,
                        const TcParams p) {
   constexpr int TW = 32, TH = 8;
-  using SL = K5Smem<POOL, OUT_F32>;
+  using SL = K5Smem<POOL, OUT_F32, G>;
+  constexpr int STAGES = SL::STAGES;
+  constexpr uint32_t SBO = 4 * G * 128;              // bytes between 8-row groups (4G K chunks of 128 B)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sg = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + SL::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (K5_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * K5_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * K5_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * K5_STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + SL::BAR_OFFSET + 8 * (2 * K5_STAGES + 4));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + SL::BAR_OFFSET + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // resident A tiles: row = output channel (zero rows beyond Cout), 16-byte K chunk j holds packed words 4j..4j+3
-  for (int i = threadIdx.x; i < p.m_tiles * TILE_M * 4; i += K5_THREADS) {
-    const int j = i & 3;
-    const int row = i >> 2;
-    uint32_t wd[4] = {0, 0, 0, 0};
-    if (row < p.cout) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(wpk) + (long long)row * 9;
+  // resident A tile(s): 16-byte K chunk j of row m; G = 1: row = channel, chunks 0..2 = packed words 0..8;
+  // G = 2: row 64 g + c holds channel c's words in chunks 4g..4g+2 and zeros elsewhere (block diagonal)
+  {
+    const int rows = (G == 1) ? p.m_tiles * TILE_M : TILE_M;
+    for (int i = threadIdx.x; i < rows * 4 * G; i += K5_THREADS) {
+      const int j = i % (4 * G);
+      const int row = i / (4 * G);
+      const int ch = (G == 1) ? row : (row % (TILE_M / G));
+      const int g = (G == 1) ? 0 : (row / (TILE_M / G));
+      const int jj = j - 4 * g;                    // chunk index inside this row's own K block
+      uint32_t wd[4] = {0, 0, 0, 0};
+      if (ch < p.cout && jj >= 0 && jj < 4) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(wpk) + (long long)ch * 9;
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (4 * j + b < 9) wd[b] = __ldg(src + 4 * j + b);
+        for (int b = 0; b < 4; ++b)
+          if (4 * jj + b < 9) wd[b] = __ldg(src + 4 * jj + b);
+      }
+      const int mt = row / TILE_M, r = row % TILE_M;
+      *reinterpret_cast<uint4*>(sg + SL::A_OFFSET + mt * (TILE_M * K5_KB * G) + (r >> 3) * SBO + j * 128 + (r & 7) * 16) =
+          make_uint4(wd[0], wd[1], wd[2], wd[3]);
     }
-    const int mt = row / TILE_M, r = row % TILE_M;
-    *reinterpret_cast<uint4*>(sg + SL::A_OFFSET + mt * (TILE_M * K5_KB) + (r >> 3) * 512 + j * 128 + (r & 7) * 16) =
-        make_uint4(wd[0], wd[1], wd[2], wd[3]);
   }
-  // zero what the producers never write: the 4th K chunk of every B row, and halo pixels -1 and 32
-  for (int i = threadIdx.x; i < K5_STAGES * TILE_N; i += K5_THREADS) {
-    const int st = i / TILE_N, pix = i % TILE_N;
-    *reinterpret_cast<uint4*>(sg + SL::B_OFFSET + st * K5_B_BYTES + (pix >> 3) * 512 + 3 * 128 + (pix & 7) * 16) = make_uint4(0, 0, 0, 0);
+  // zero what the producers never write: the 4th K chunk of every pixel group, and halo pixels -1 and 32
+  for (int i = threadIdx.x; i < STAGES * TILE_N * G; i += K5_THREADS) {
+    const int g = i % G;
+    const int pix = (i / G) % TILE_N;
+    const int st = i / (G * TILE_N);
+    *reinterpret_cast<uint4*>(sg + SL::B_OFFSET + st * SL::B_BYTES + (pix >> 3) * SBO + (4 * g + 3) * 128 + (pix & 7) * 16) =
+        make_uint4(0, 0, 0, 0);
   }
-  for (int i = threadIdx.x; i < 2 * 10 * 2; i += K5_THREADS) {
+  for (int i = threadIdx.x; i < 2 * SL::HALO_ROWS * 2; i += K5_THREADS) {
     const int row = i >> 1, side = i & 1;
     *reinterpret_cast<uint32_t*>(sg + SL::HALO_OFFSET + row * K5_ROW_PITCH + (side ? 16 + 4 * 32 : 12)) = 0u;
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < K5_STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCERS); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -521,59 +545,70 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint64_t a_desc = make_smem_desc_interleaved(smem_base + SL::A_OFFSET + mt * (TILE_M * K5_KB), 128, 512);
-        const uint64_t b_desc = make_smem_desc_interleaved(smem_base + SL::B_OFFSET + stage * K5_B_BYTES, 128, 512);
-        // K step k covers chunks 2k, 2k+1: advance the start address by 256 B
-        umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc, b_desc, idesc, 0u);
-        umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc + 16u, b_desc + 16u, idesc, 1u);
+        const uint64_t a_desc = make_smem_desc_interleaved(smem_base + SL::A_OFFSET + mt * (TILE_M * K5_KB * G), 128, SBO);
+        const uint64_t b_desc = make_smem_desc_interleaved(smem_base + SL::B_OFFSET + stage * SL::B_BYTES, 128, SBO);
+        // K step k covers chunks 2k, 2k+1: advance the start address by 256 B (16 units of 16 B)
+#pragma unroll
+        for (int k = 0; k < 2 * G; ++k)
+          umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc + (uint64_t)(16 * k), b_desc + (uint64_t)(16 * k), idesc, k > 0 ? 1u : 0u);
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
-        if (++stage == K5_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), sg + SL::STG_OFFSET,
-                                                            warp, lane);
+    epilogue_role<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH, G>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
+                                                               sg + SL::STG_OFFSET, warp, lane);
   } else if (warp >= 4 + NUM_EPI_WARPS) {
     // ===================== im2col producers (128 threads) =====================
     const int t = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
-    // halo staging work item of this thread: image row `hrow` (0..9), pixel group `grp` (4 pixels = 3 words)
-    const bool loader = t < 80;
-    const int hrow = t >> 3, grp = t & 7;
-    uint32_t g0 = 0, g1 = 0, g2 = 0;
+    // halo staging: work item = (image row hrow of the halo, pixel group of 4 = 3 words)
+    constexpr int ITEMS = SL::HALO_ROWS * 8;
+    constexpr int PER = (ITEMS + K5_PRODUCERS - 1) / K5_PRODUCERS;
+    uint32_t g0[PER], g1[PER], g2[PER];
     auto issue_loads = [&](int tile) {
-      if (!loader) return;
       int pt = tile / p.m_tiles;
       const int th_i = pt % p.tiles_h;
       const int nimg = pt / p.tiles_h;
-      const int gh = th_i * TH - 1 + hrow;
-      g0 = g1 = g2 = 0;
-      if (gh >= 0 && gh < p.h) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((long long)nimg * p.h + gh) * (TW * 3)) + grp * 3;
-        g0 = __ldg(src); g1 = __ldg(src + 1); g2 = __ldg(src + 2);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int item = t + u * K5_PRODUCERS;
+        const int hrow = item >> 3, grp = item & 7;
+        const int gh = th_i * (TH * G) - 1 + hrow;
+        g0[u] = g1[u] = g2[u] = 0;
+        if (item < ITEMS && gh >= 0 && gh < p.h) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((long long)nimg * p.h + gh) * (TW * 3)) + grp * 3;
+          g0[u] = __ldg(src); g1[u] = __ldg(src + 1); g2[u] = __ldg(src + 2);
+        }
       }
     };
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     if (blockIdx.x < p.num_tiles) issue_loads(blockIdx.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      uint8_t* halo = sg + SL::HALO_OFFSET + (it & 1) * K5_HALO_BYTES;
-      if (loader) {
-        // 12 RGB bytes -> 4 RGBX words
-        const uint32_t p0 = g0 & 0x00FFFFFFu;
-        const uint32_t p1 = (g0 >> 24) | ((g1 & 0x0000FFFFu) << 8);
-        const uint32_t p2 = (g1 >> 16) | ((g2 & 0x000000FFu) << 16);
-        const uint32_t p3 = g2 >> 8;
-        *reinterpret_cast<uint4*>(halo + hrow * K5_ROW_PITCH + 16 + grp * 16) = make_uint4(p0, p1, p2, p3);
+      uint8_t* halo = sg + SL::HALO_OFFSET + (it & 1) * SL::HALO_BYTES;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int item = t + u * K5_PRODUCERS;
+        if (item < ITEMS) {
+          // 12 RGB bytes -> 4 RGBX words
+          const uint32_t p0 = g0[u] & 0x00FFFFFFu;
+          const uint32_t p1 = (g0[u] >> 24) | ((g1[u] & 0x0000FFFFu) << 8);
+          const uint32_t p2 = (g1[u] >> 16) | ((g2[u] & 0x000000FFu) << 16);
+          const uint32_t p3 = g2[u] >> 8;
+          *reinterpret_cast<uint4*>(halo + (item >> 3) * K5_ROW_PITCH + 16 + (item & 7) * 16) = make_uint4(p0, p1, p2, p3);
+        }
       }
       named_bar_sync(1, K5_PRODUCERS);
       if (tile + (int)gridDim.x < p.num_tiles) issue_loads(tile + gridDim.x);      // prefetch the next tile's rows
       mbar_wait(empty_bar(stage), phase ^ 1u);
-      uint8_t* btile = sg + SL::B_OFFSET + stage * K5_B_BYTES;
+      uint8_t* btile = sg + SL::B_OFFSET + stage * SL::B_BYTES;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int pix = t + q * 128;                 // tile pixel = column of the accumulator
-        const int th = pix >> 5, tw = pix & 31;
+      for (int q = 0; q < 2 * G; ++q) {
+        const int gpix = t + q * K5_PRODUCERS;       // pixel of the (8G x 32) tile
+        const int g = gpix >> 8;                     // pixel group = 8-row block
+        const int pix = gpix & 255;                  // accumulator column
+        const int th = gpix >> 5, tw = gpix & 31;
         uint32_t k[12];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -581,14 +616,14 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
           k[3 * r + 0] = hp[0]; k[3 * r + 1] = hp[1]; k[3 * r + 2] = hp[2];
         }
         k[9] = k[10] = k[11] = 0;
-        uint4* dst = reinterpret_cast<uint4*>(btile + (pix >> 3) * 512 + (pix & 7) * 16);
+        uint4* dst = reinterpret_cast<uint4*>(btile + (pix >> 3) * SBO + (4 * g) * 128 + (pix & 7) * 16);
         dst[0] = make_uint4(k[0], k[1], k[2], k[3]);
         dst[8] = make_uint4(k[4], k[5], k[6], k[7]);
         dst[16] = make_uint4(k[8], k[9], k[10], k[11]);
       }
       fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
       mbar_arrive(full_bar(stage));
-      if (++stage == K5_STAGES) { stage = 0; phase ^= 1u; }
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   }
 
@@ -692,24 +727,26 @@ bool first_layer_shape(const qnnb_conv_desc& d) {
 int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
+  const bool pool = d.epi.pool == 2;
+  const bool f32 = d.epi.act == QNNB_ACT_NONE;
+  // two pixel groups per tile when the accumulator lanes would otherwise be half empty
+  const int G = (!f32 && d.cout == 64 && d.h % 16 == 0) ? 2 : 1;
   TcParams p;
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
   p.tiles_w = 1;
-  p.tiles_h = d.h / 8;
+  p.tiles_h = d.h / (8 * G);
   p.tiles_n = d.n;
-  p.m_tiles = ceil_div(d.cout, TILE_M);
+  p.m_tiles = (G == 2) ? 1 : ceil_div(d.cout, TILE_M);
   p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
   p.kchunks = 1;
   p.out_pitch = d.cout < TILE_M ? d.cout : TILE_M;
   p.y = y;
   p.epi = make_epi(d.epi);
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  const bool pool = d.epi.pool == 2;
-  const bool f32 = d.epi.act == QNNB_ACT_NONE;
   CUtensorMap my;
   memset(&my, 0, sizeof(my));
   if (!f32) {
-    Geometry g = {32, 8, 1};
+    Geometry g = {32, 8 * G, 1};
     int rc = make_output_map(encode, &my, y, d.n, pool ? d.h / 2 : d.h, pool ? d.w / 2 : d.w, d.cout, p.out_pitch, g, pool);
     if (rc) return rc;
   }
@@ -719,17 +756,17 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
     QNNB_CUDA(cudaGetLastError());
     return QNNB_OK;
   };
-  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true, 0>, K5Smem<false, true>::TOTAL);
+  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true, 0, 1>, K5Smem<false, true, 1>::TOTAL);
+  if (G == 2) {
+    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64, 2>, K5Smem<true, false, 2>::TOTAL);
+    return go(conv3x3_u8c3_tc_kernel<false, false, 64, 2>, K5Smem<false, false, 2>::TOTAL);
+  }
   if (p.out_pitch == 128) {
-    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 128>, K5Smem<true, false>::TOTAL);
-    return go(conv3x3_u8c3_tc_kernel<false, false, 128>, K5Smem<false, false>::TOTAL);
+    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 128, 1>, K5Smem<true, false, 1>::TOTAL);
+    return go(conv3x3_u8c3_tc_kernel<false, false, 128, 1>, K5Smem<false, false, 1>::TOTAL);
   }
-  if (p.out_pitch == 64) {
-    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64>, K5Smem<true, false>::TOTAL);
-    return go(conv3x3_u8c3_tc_kernel<false, false, 64>, K5Smem<false, false>::TOTAL);
-  }
-  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 0>, K5Smem<true, false>::TOTAL);
-  return go(conv3x3_u8c3_tc_kernel<false, false, 0>, K5Smem<false, false>::TOTAL);
+  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 0, 1>, K5Smem<true, false, 1>::TOTAL);
+  return go(conv3x3_u8c3_tc_kernel<false, false, 0, 1>, K5Smem<false, false, 1>::TOTAL);
 }
 
 }  // namespace

@@ -368,7 +368,9 @@ def test_conv2d_tcgen05_bit_exact(case):
 K5_CASES = [
     # n, h, cout, nb, abits, pool, f32_out
     (1, 32, 64, 4, 4, False, True),
-    (3, 32, 64, 4, 4, True, False),       # cfg3 layer 1
+    (3, 32, 64, 4, 4, True, False),       # cfg3 layer 1 (two pixel groups per tile)
+    (2, 32, 64, 8, 8, False, False),      # two pixel groups, un-pooled
+    (2, 16, 64, 4, 4, True, False),       # 16 rows = exactly one two-group tile per image
     (2, 32, 256, 8, 8, False, False),     # cfg4 layer 1 (two channel tiles)
     (2, 32, 32, 4, 4, False, False),      # narrow layer: one active lane quarter, runtime row pitch
     (3, 16, 128, 2, 2, True, False),      # non-square map, 32 wide
