@@ -234,27 +234,48 @@ def run_ours(args):
     xs = host[0][:8].numpy()
     ok = bool(np.array_equal(model.predict(xs, impl=impl), exact.forward(nodes, xs)))
 
-    # ---- CUDA graphs: one per input buffer, sharing a memory pool
+    # ---- CUDA graphs: one per input buffer.  Consecutive steps are independent batches, so they are replayed
+    # round-robin on NS streams (graph i always on stream i % NS, with that stream's private memory pool): the
+    # tail of one batch overlaps the head of the next, as in a serving loop.
+    NS = args.streams if args.streams > 0 else (1 if args.workload == "cfg4" else 4)
     graphs = None
-    if args.graphs and world == 1:
-        graphs = []
-        pool = torch.cuda.graph_pool_handle()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for b in bufs:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=s):
-                    o = plan.forward(b)
+    streams = [torch.cuda.Stream() for _ in range(NS)]
+    if args.graphs:
+        try:
+            graphs = []
+            pools = [torch.cuda.graph_pool_handle() for _ in range(NS)]
+            for i, b in enumerate(bufs):
+                st = streams[i % NS]
+                st.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(st):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pools[i % NS], stream=st):
+                        o = step_fn(b)
                 graphs.append((g, o))
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+        except Exception as exc:                       # e.g. a collective that cannot be captured
+            if rank == 0:
+                print("graph capture failed (%s): falling back to eager launches" % exc, file=sys.stderr)
+            graphs = None
+            torch.cuda.synchronize()
+    nround = (nbuf // NS) * NS                         # keeps graph index -> stream mapping fixed
 
     def run_step(i):
-        if graphs is not None:
-            graphs[i % nbuf][0].replay()
-        else:
-            step_fn(bufs[i % nbuf])
+        j = i % nround
+        with torch.cuda.stream(streams[j % NS]):
+            if graphs is not None:
+                graphs[j][0].replay()
+            else:
+                step_fn(bufs[j])
+
+    def fence_all(ev=None):
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            cur.wait_stream(st)
+        if ev is not None:
+            ev.record()
+        for st in streams:
+            st.wait_stream(cur)
 
     for i in range(max(args.warmup, 3)):
         run_step(i)
@@ -264,10 +285,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        e0.record()
+        fence_all(e0)
         for i in range(args.steps):
             run_step(i)
-        e1.record()
+        fence_all(e1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -325,15 +346,22 @@ def run_ours(args):
                 "traffic": None, "kernel": name, "kernel_ms": float(per[dom]), "peak_source": pk["source"] + " copy bandwidth"}
     roof["per_kernel_ms"] = {w[0]: float(p) for w, p in zip(work, per)}
 
-    # ---- end to end through the public API: pinned host batch -> predict -> host logits, every step
+    # ---- end to end through the public API: pinned host batch -> H2D -> fused plan (CUDA graph) -> D2H logits,
+    # every step; steps are software-pipelined three deep (model.predict_async), as a serving loop would.
     torch.cuda.synchronize()
     for i in range(3):
         model.predict(host[i % len(host)], impl=impl)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
+    pending = []
+    checksum = 0.0
     for i in range(args.steps):
-        res = model.predict(host[i % len(host)], impl=impl)
+        pending.append(model.predict_async(host[i % len(host)], impl=impl))
+        if len(pending) >= 3:
+            checksum += float(pending.pop(0).result()[0, 0])
+    for h in pending:
+        checksum += float(h.result()[0, 0])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -355,7 +383,7 @@ def run_ours(args):
                                args.workload, cf.network_type, cf.wbits, cf.abits, cf.nla, cf.nlb, cf.nlc, cf.nfa, cf.nfb, cf.nfc, batch),
                            "global_batch": batch * world, "parallelism": "batch-sharded x%d, NCCL logit all-gather" % world,
                            "l2_policy": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotated every step" % (nbuf, nbuf * batch * img_bytes / 1e6),
-                           "cuda_graphs": graphs is not None, "kernels": args.kernels,
+                           "cuda_graphs": graphs is not None, "streams": NS, "kernels": args.kernels,
                            "parity_vs_exact_oracle": ok},
                 "clocks": clk.summary(), "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": batch * img_bytes,
@@ -378,6 +406,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--kernels", default="auto", choices=["auto", "generic", "tcgen05"])
     ap.add_argument("--graphs", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=0, help="0 = auto: 4 for short steps, 1 for the large config")
     ap.add_argument("--ref-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -51,18 +51,35 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// latency-critical wait (TMA producer / MMA issuer: one thread each): plain try_wait spin
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > (1u << 24)) __trap();     // a broken pipeline must fault, not hang the GPU
+    if (++spins > (1u << 26)) __trap();     // a broken pipeline must fault, not hang the GPU
+  }
+}
+// many-thread wait (epilogue / im2col warps): let the hardware park the warp (suspend-time hint, ns) instead of
+// burning issue slots the MMA-feeding warps could use
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 20000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -228,7 +245,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
       if (leader) tma_store_wait_read();
       named_bar_sync(EPI_BAR_ID, EPI_THREADS);
     }
-    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    mbar_wait_parked(tfull0 + 8u * acc, acc_phase);
     tc_fence_after();
     if (warp_active) {
 #pragma unroll 1
@@ -601,7 +618,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
       }
       named_bar_sync(1, K5_PRODUCERS);
       if (tile + (int)gridDim.x < p.num_tiles) issue_loads(tile + gridDim.x);      // prefetch the next tile's rows
-      mbar_wait(empty_bar(stage), phase ^ 1u);
+      mbar_wait_parked(empty_bar(stage), phase ^ 1u);
       uint8_t* btile = sg + SL::B_OFFSET + stage * SL::B_BYTES;
 #pragma unroll
       for (int q = 0; q < 2 * G; ++q) {

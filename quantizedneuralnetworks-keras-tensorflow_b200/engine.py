@@ -414,6 +414,32 @@ class _ModelBase:
         feeds the reference."""
         return self.plan(impl).predict(x, batch_size=batch_size, return_logits=return_logits)
 
+    def evaluate(self, x, y, batch_size=None, verbose=0, loss=None):
+        """``model.evaluate`` as used at train.py:163-169: returns ``[loss, accuracy]``.  ``y`` is one-hot
+        (ResNet, categorical cross-entropy, train.py:101-107) or +-1 targets (VGG, squared hinge, train.py:68-100,
+        utils/load_data.py:63-66); ``loss`` overrides the choice ('categorical_crossentropy' | 'squared_hinge').
+        The forward pass runs on the GPU; the reduction over N x classes scores is host arithmetic."""
+        import numpy as np
+        scores = self.predict(x, batch_size=batch_size)
+        scores = scores if isinstance(scores, np.ndarray) else scores.detach().cpu().numpy()
+        y = np.asarray(y, dtype=np.float32)
+        if loss is None:
+            loss = "squared_hinge" if y.min() < 0 else "categorical_crossentropy"
+        if loss == "squared_hinge":
+            lv = float(np.mean(np.maximum(1.0 - y * scores, 0.0) ** 2))
+        elif loss == "categorical_crossentropy":
+            p = np.clip(scores / scores.sum(axis=1, keepdims=True), 1e-7, 1 - 1e-7)
+            lv = float(np.mean(-(y * np.log(p)).sum(axis=1)))
+        else:
+            raise ValueError("unsupported loss %r" % loss)
+        acc = float(np.mean(scores.argmax(1) == y.argmax(1)))
+        return [lv, acc]
+
+    def predict_async(self, x, impl=0):
+        """Pipelined variant for host batches: enqueue H2D copy + CUDA-graph replay + D2H copy on one of the
+        plan's streams and return a handle; ``handle.result()`` gives the fp32 (N, classes) CPU tensor."""
+        return self.plan(impl).predict_async(x)
+
 
 
 class Sequential(_ModelBase):

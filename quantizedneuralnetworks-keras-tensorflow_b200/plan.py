@@ -34,6 +34,21 @@ def _act_of(layer):
     return None
 
 
+class _Handle:
+    """Result of Plan.predict_async: ``result()`` waits for the slot's D2H copy and returns a private copy."""
+
+    def __init__(self, slot):
+        self._slot = slot
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            self._slot["event"].synchronize()
+            self._out = self._slot["host"].clone()
+            self._slot["busy"] = False
+        return self._out
+
+
 class Plan:
     def __init__(self, model, impl=L.IMPL_AUTO):
         self.model = model
@@ -45,7 +60,10 @@ class Plan:
         self.output_idx = self.index[id(outs[0])]
         self.steps = []
         self.launches = 0
+        self.launches_per_forward = 0
+        self._slots = {}
         self._compile()
+        self.launches_per_forward = len(self.steps)
 
     # ------------------------------------------------------------------ compile
     def _consumers(self):
@@ -264,8 +282,69 @@ class Plan:
             return out, env.get("logits", out)
         return out
 
+    # ------------------------------------------------------------------ pipelined host path
+    # A host batch goes through one of PIPELINE_DEPTH slots: its own stream, a static device input, the whole
+    # fused plan captured once as a CUDA graph, and a pinned result buffer.  H2D copy, graph replay and D2H
+    # copy are enqueued back to back on the slot's stream, so consecutive batches overlap copy and compute.
+    PIPELINE_DEPTH = 3
+
+    def _slot(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        ring = self._slots.setdefault(key, {"slots": [], "next": 0})
+        if len(ring["slots"]) < self.PIPELINE_DEPTH:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            st = torch.cuda.Stream()
+            x_dev = torch.zeros(shape, dtype=dtype, device=dev)
+            if not ring["slots"]:
+                self.forward(x_dev)                     # packs weights / uploads constants outside the capture
+                torch.cuda.synchronize()
+            st.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(g, stream=st):
+                    out_dev = self.forward(x_dev)
+            out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype).pin_memory()
+            ring["slots"].append({"stream": st, "x": x_dev, "graph": g, "out": out_dev, "host": out_host,
+                                  "event": torch.cuda.Event(), "busy": False})
+        slot = ring["slots"][ring["next"] % len(ring["slots"])] if len(ring["slots"]) == self.PIPELINE_DEPTH else ring["slots"][-1]
+        ring["next"] += 1
+        return slot
+
+    def predict_async(self, x):
+        """Enqueue one host batch (numpy array or CPU tensor, ideally pinned) and return a handle whose
+        ``result()`` blocks until the logits are back in host memory.  At most PIPELINE_DEPTH handles may be
+        outstanding: a slot is recycled (after waiting for it) when the ring wraps around."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("predict needs a CUDA device: this package has no CPU path")
+        src = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x.contiguous()
+        if src.is_cuda:
+            raise ValueError("predict_async takes host batches; use predict() for device tensors")
+        slot = self._slot(src.shape, src.dtype)
+        if slot["busy"]:
+            slot["event"].synchronize()
+        slot["busy"] = True
+        with torch.cuda.stream(slot["stream"]):
+            slot["x"].copy_(src, non_blocking=True)
+            slot["graph"].replay()
+            slot["host"].copy_(slot["out"], non_blocking=True)
+            slot["event"].record(slot["stream"])
+        self.launches += self.launches_per_forward
+        return _Handle(slot)
+
     def predict(self, x, batch_size=None, return_logits=False):
         as_numpy = isinstance(x, np.ndarray)
+        if not return_logits and (as_numpy or (isinstance(x, torch.Tensor) and not x.is_cuda)) and int(x.shape[0]) > 0:
+            n = int(x.shape[0])
+            bs = int(batch_size) if batch_size else min(n, MAX_CHUNK)
+            if n % bs == 0 or n < bs:
+                handles, outs = [], []
+                for s in range(0, n, bs):
+                    handles.append(self.predict_async(x[s:s + bs]))
+                    if len(handles) >= self.PIPELINE_DEPTH:
+                        outs.append(handles.pop(0).result())
+                outs.extend(h.result() for h in handles)
+                out = torch.cat(outs) if len(outs) > 1 else outs[0]
+                return out.numpy() if as_numpy else out
         host_tensor = (not as_numpy) and isinstance(x, torch.Tensor) and not x.is_cuda
         if as_numpy or host_tensor:
             if not torch.cuda.is_available():

@@ -83,3 +83,31 @@ def assign_weights_from_spec(model, nodes):
     for lay, nd in zip(prod_bn, spec_bns):
         lay.set_weights([nd["gamma"], nd["beta"], nd["mean"], nd["var"]])
     model._invalidate()
+
+
+def spec_weights_from_model(model, nodes):
+    """The inverse of assign_weights_from_spec: copy the product model's weights into an oracle spec."""
+    from qnn_b200 import engine as E
+    from qnn_b200.layers._base import QConv2DBase, QDenseBase
+    order = E.topo_order(model._graph()[1])
+    spec_convs = [nd for nd in nodes if nd["op"] in ("conv", "dense")]
+    spec_bns = [nd for nd in nodes if nd["op"] == "bn"]
+    prod_lin = [t.layer for t in order if isinstance(t.layer, (QConv2DBase, QDenseBase))]
+    prod_bn = [t.layer for t in order if isinstance(t.layer, E.BatchNormalization)]
+    prod_lin.sort(key=lambda l: int(l.name.rsplit("_", 1)[1]) + (10000 if isinstance(l, QDenseBase) else 0))
+    prod_bn.sort(key=lambda l: int(l.name.rsplit("_", 1)[1]))
+    assert len(prod_lin) == len(spec_convs) and len(prod_bn) == len(spec_bns)
+    for lay, nd in zip(prod_lin, spec_convs):
+        assert tuple(lay.kernel.shape) == tuple(weight_shape(nd))
+        nd["kernel"] = lay.kernel
+        if nd["use_bias"]:
+            nd["bias"] = lay.bias
+    for lay, nd in zip(prod_bn, spec_bns):
+        nd["gamma"], nd["beta"], nd["mean"], nd["var"] = lay.get_weights()
+    return nodes
+
+
+def weight_shape(nd):
+    if nd["op"] == "conv":
+        return (nd["ksize"], nd["ksize"], nd["cin"], nd["filters"])
+    return (nd["fin"], nd["units"])

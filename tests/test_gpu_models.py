@@ -194,3 +194,49 @@ def test_layer_objects_standalone_call():
     assert np.abs(z - want).max() <= 1e-4 * np.abs(want).max()
     with pytest.raises(ValueError):
         QuantizedConv2D(filters=4, kernel_size=3, padding='same')(q.Input(shape=(8, 8, None)))
+
+
+# --------------------------------------------------------------------------- trained weights (reference checkpoints)
+def _trained(code, nt):
+    import os
+    import qnn_b200 as q
+    from helpers import spec_weights_from_model
+    q.reset_names()
+    cf = make_cf(network_type=nt, wbits=4, abits=4, architecture='RESNET', nres=3, kernel_initializer='he_normal', kernel_regularizer=1e-4)
+    model = q.build_model(cf, legacy_resnet=True)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trained_resnet3_%s.npz" % code))
+    model.set_weights([g["w%03d" % i] for i in range(len(g.files) - 1)])
+    nodes = netspec.build_spec(cf, use_bias=True, half=False)
+    spec_weights_from_model(model, nodes)
+    return cf, model, nodes
+
+
+@pytest.mark.parametrize("code,nt", [("44", "full-qnn"), ("bb", "full-bnn")])
+def test_trained_reference_checkpoints_bit_exact(code, nt):
+    """The reference's own trained ResNet-20 checkpoints (results/RESNET3/weights_{44,bb}.hdf5, converted by
+    tests/golden/make_trained_fixture.py): real weight / BatchNorm statistics, older biased graph revision.
+    Logits bit-exact vs O1 on noise and on smooth images; tolerance vs the fp32 restatement."""
+    cf, model, nodes = _trained(code, nt)
+    rng = np.random.default_rng(77)
+    noise = rng.integers(0, 256, size=(32, 32, 32, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:32, 0:32]
+    smooth = np.stack([np.stack([(127 + 120 * np.sin(xx / (3 + i) + c) * np.cos(yy / (4 + i))) for c in range(3)], -1) for i in range(16)])
+    for x in (noise, smooth.astype(np.uint8)):
+        want, vals, info = exact.forward(nodes, x, return_all=True)
+        got, logits = model.predict(x, return_logits=True)
+        assert np.array_equal(logits, info["logits"]), "max abs logit diff %g" % np.abs(logits - info["logits"]).max()
+        assert np.array_equal(got.argmax(1), want.argmax(1))
+        o2b = refstate.forward(nodes, x, trick=False)
+        assert rel_err(got, o2b) <= 1e-4 and (got.argmax(1) == o2b.argmax(1)).mean() >= 0.999
+
+
+def test_evaluate_matches_host_metrics():
+    cf, model, nodes = _trained("44", "full-qnn")
+    x = images(cf, 64)
+    labels = np.random.default_rng(3).integers(0, 10, size=64)
+    y = np.eye(10, dtype=np.float32)[labels]
+    loss, acc = model.evaluate(x, y)
+    p = exact.forward(nodes, x)
+    assert abs(acc - float((p.argmax(1) == labels).mean())) < 1e-9
+    want_loss = float(np.mean(-np.log(np.clip(p[np.arange(64), labels], 1e-7, 1))))
+    assert abs(loss - want_loss) <= 1e-4 * max(want_loss, 1.0)

@@ -181,3 +181,29 @@ def test_sharded_predict_over_gloo_world_size_2():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(ok for _, ok in res)
+
+
+def test_hdf5_reader_on_reference_checkpoint():
+    """Pure-Python HDF5 reader against a real Keras checkpoint of the reference (build container only) and against
+    the converted fixture that travels with the repo."""
+    ref = "/root/reference/results/RESNET3/weights_44.hdf5"
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trained_resnet3_44.npz"))
+    names = list(gold["names"])
+    assert len(names) == 120 and names[0] == "quantized_conv2d_1/kernel"
+    assert sum(gold["w%03d" % i].size for i in range(120)) == 274442
+    if not os.path.exists(ref):
+        pytest.skip("reference checkpoints are only present in the build container")
+    from qnn_b200.hdf5_lite import read_keras_weights
+    t = read_keras_weights(ref)
+    assert len(t) == 41 and sum(a.size for v in t.values() for a in v.values()) == 274442
+    assert t["quantized_conv2d_1"]["kernel"].shape == (3, 3, 3, 16)
+    assert abs(float(t["quantized_conv2d_1"]["kernel"].max()) - 0.9385) < 1e-3        # SURVEY.md App. D
+    assert t["quantized_dense_2"]["kernel"].shape == (64, 10)
+    q.reset_names()
+    m = q.build_model(make_cf(architecture="RESNET", nres=3), legacy_resnet=True)
+    m.load_weights(ref)
+    for i, w in enumerate(m.get_weights()):
+        assert np.array_equal(w, gold["w%03d" % i])
+    with pytest.raises(ValueError):
+        q.reset_names()
+        q.build_model(make_cf(architecture="RESNET", nres=5), legacy_resnet=True).load_weights(ref)
