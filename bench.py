@@ -238,6 +238,12 @@ def run_ours(args):
     # round-robin on NS streams (graph i always on stream i % NS, with that stream's private memory pool): the
     # tail of one batch overlaps the head of the next, as in a serving loop.
     NS = args.streams if args.streams > 0 else (1 if args.workload == "cfg4" else 4)
+    # world > 1: the per-step NCCL logit gather is issued eagerly from ONE dedicated communication stream, in step
+    # order on every rank (a communicator must see the same sequence everywhere); forward graphs keep overlapping.
+    comm = torch.cuda.Stream() if world > 1 else None
+    gather_flat = torch.empty((world * batch, cf.classes), dtype=torch.float32, device=dev) if world > 1 else None
+    last_comm = [None] * NS
+    fwd_done = [torch.cuda.Event() for _ in range(NS)]
     graphs = None
     streams = [torch.cuda.Stream() for _ in range(NS)]
     if args.graphs:
@@ -250,7 +256,7 @@ def run_ours(args):
                 with torch.cuda.stream(st):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=pools[i % NS], stream=st):
-                        o = step_fn(b)
+                        o = plan.forward(b)          # the NCCL gather stays outside the graph (issued eagerly below)
                 graphs.append((g, o))
             torch.cuda.synchronize()
         except Exception as exc:                       # e.g. a collective that cannot be captured
@@ -264,17 +270,28 @@ def run_ours(args):
         j = i % nround
         with torch.cuda.stream(streams[j % NS]):
             if graphs is not None:
+                if world > 1 and last_comm[j % NS] is not None:
+                    streams[j % NS].wait_event(last_comm[j % NS])      # previous logits of this stream's pool were gathered
                 graphs[j][0].replay()
+                if world > 1:
+                    fwd_done[j % NS].record(streams[j % NS])
+                    comm.wait_event(fwd_done[j % NS])
+                    with torch.cuda.stream(comm):
+                        dist.all_gather_into_tensor(gather_flat, graphs[j][1])
+                        ev = torch.cuda.Event()
+                        ev.record(comm)
+                    last_comm[j % NS] = ev
             else:
                 step_fn(bufs[j])
 
     def fence_all(ev=None):
         cur = torch.cuda.current_stream()
-        for st in streams:
+        everyone = streams + ([comm] if comm is not None else [])
+        for st in everyone:
             cur.wait_stream(st)
         if ev is not None:
             ev.record()
-        for st in streams:
+        for st in everyone:
             st.wait_stream(cur)
 
     for i in range(max(args.warmup, 3)):
