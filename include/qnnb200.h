@@ -60,7 +60,8 @@ extern "C" {
 /* kernel selection (testing / profiling) */
 #define QNNB_IMPL_AUTO    0
 #define QNNB_IMPL_GENERIC 1    /* CUDA-core dp4a / popc / FFMA tiles      */
-#define QNNB_IMPL_TCGEN05 2    /* tcgen05.mma kind::i8 + TMA + TMEM       */
+#define QNNB_IMPL_TCGEN05 2    /* tcgen05.mma kind::i8 + TMA + TMEM (halo-resident implicit GEMM) */
+#define QNNB_IMPL_TCGEN05_V1 3 /* first-generation tcgen05 kernel (one TMA box per filter tap); kept for A/B profiling */
 
 /*
  * The fused epilogue applied to every accumulator (fixed op order, every step a separate
@@ -165,6 +166,13 @@ int qnnb_leaky_f32(const float* x, int64_t count, float alpha, float* y, void* s
 int qnnb_round_f32(const float* x, int64_t count, float* y, void* stream);
 /* int8 levels / packed bits -> fp32 values (level * scale, or +-1) */
 int qnnb_dequantize(int32_t kind, const void* x, int64_t count, int32_t channels, float scale, float* y, void* stream);
+
+/*
+ * Profiling aid (not part of the inference path): register a device buffer of `nwords` uint64 (word 0 = event
+ * counter, must be zeroed) in which CTA 0 of the tcgen05 conv kernel records (tag<<32|tile, globaltimer ns) pairs
+ * for its pipeline events; NULL switches tracing off.  Process-wide, not thread-safe.
+ */
+int qnnb_debug_set_trace(void* buf, int64_t nwords);
 
 #ifdef __cplusplus
 }

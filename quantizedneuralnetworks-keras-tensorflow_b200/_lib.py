@@ -17,7 +17,7 @@ KIND_NONE, KIND_U8, KIND_I8, KIND_B1, KIND_F32 = -1, 0, 1, 2, 3
 W_QUANT, W_BINARY, W_TERNARY = 0, 1, 2
 WFMT_I8, WFMT_B1 = 0, 1
 ACT_NONE, ACT_QUANT, ACT_SIGN, ACT_LEAKY = 0, 1, 2, 3
-IMPL_AUTO, IMPL_GENERIC, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_GENERIC, IMPL_TCGEN05, IMPL_TCGEN05_V1 = 0, 1, 2, 3
 EINVAL, ECUDA, EUNSUPPORTED = -1, -2, -3
 
 
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "qnnb_maxpool2_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "qnnb_leaky_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "qnnb_round_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "qnnb_debug_set_trace": (C.c_int, [C.c_void_p, C.c_int64]),
     "qnnb_dequantize": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
 }
 

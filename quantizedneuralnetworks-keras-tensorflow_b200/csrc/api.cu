@@ -105,6 +105,10 @@ int qnnb_conv2d(const qnnb_conv_desc* d, const void* x, const void* w, void* y, 
   cudaStream_t st = (cudaStream_t)stream;
   const char* why = "";
   const bool tc_ok = conv_tc_supported(*d, &why);
+  if (d->impl == QNNB_IMPL_TCGEN05_V1) {
+    if (!tc_ok || !conv_tc_v1_supported(*d)) { set_error("conv2d: tcgen05 v1 kernel does not cover this shape"); return QNNB_EUNSUPPORTED; }
+    return launch_conv_tc(*d, x, w, y, st);
+  }
   if (d->impl == QNNB_IMPL_TCGEN05) {
     if (!tc_ok) { set_error("conv2d: tcgen05 path does not cover this shape: %s", why); return QNNB_EUNSUPPORTED; }
     return launch_conv_tc(*d, x, w, y, st);
@@ -112,6 +116,11 @@ int qnnb_conv2d(const qnnb_conv_desc* d, const void* x, const void* w, void* y, 
   if (d->impl == QNNB_IMPL_AUTO && tc_ok) return launch_conv_tc(*d, x, w, y, st);
   QNNB_CHECK_ARG(d->impl == QNNB_IMPL_AUTO || d->impl == QNNB_IMPL_GENERIC, "conv2d: bad impl %d", d->impl);
   return launch_conv_generic(*d, x, w, y, st);
+}
+
+int qnnb_debug_set_trace(void* buf, int64_t nwords) {
+  set_trace_buffer((unsigned long long*)buf, (int)nwords);
+  return QNNB_OK;
 }
 
 int qnnb_dense(const qnnb_dense_desc* d, const void* x, const void* w, float* y, float* logits, void* stream) {

@@ -173,7 +173,9 @@ int launch_pack_weights(int mode, int nb, float H, const float* w, int kh, int k
                         int wfmt, void* out, float* scratch, cudaStream_t st);
 int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why);
+bool conv_tc_v1_supported(const qnnb_conv_desc& d);
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
+void set_trace_buffer(unsigned long long* buf, int cap);
 int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st);
 
 }  // namespace qnnb

@@ -186,7 +186,25 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
   return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Optional device-side timeline (debug/profiling only): when a buffer is registered with qnnb_debug_set_trace(),
+// CTA 0 records globaltimer stamps of its pipeline events as (tag, value) pairs.  NULL in production.
+struct Trace { unsigned long long* buf; int cap; };
+static Trace g_trace = {nullptr, 0};
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace(const Trace& tr, int tag, int idx) {
+  if (tr.buf != nullptr && blockIdx.x == 0) {
+    const unsigned long long slot = atomicAdd(tr.buf, 1ull);
+    if ((int)(2 * slot + 3) < tr.cap) { tr.buf[1 + 2 * slot] = ((unsigned long long)tag << 32) | (unsigned)idx; tr.buf[2 + 2 * slot] = gtime(); }
+  }
+}
+
 struct TcParams {
+  Trace tr;
   int n, h, w, cin, cout;
   int tiles_w, tiles_h, tiles_n, m_tiles, num_tiles;
   int kchunks;            // cin / KC
@@ -210,11 +228,11 @@ struct StageTile {
 // FOLD: acc_scale is a power of two (see QConst); PITCH: bytes per staged row (0 = runtime p.out_pitch).
 // GROUPS (K5 only, TW = 32): when Cout <= 64 the 128 TMEM lanes hold GROUPS = 2 pixel groups of 64 channels --
 // lane L is channel L % 64 of the pixels 8*(L / 64) rows further down, so one tile covers 16 image rows.
-template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1>
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1, int TH_ = 0>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, uint8_t* stg, int warp, int lane) {
-  constexpr int TH = (TW == 32) ? 8 : (TW == 16 ? 16 : 8);
-  constexpr int TN = (TW == 8) ? 4 : 1;
+  constexpr int TH = TH_ ? TH_ : ((TW == 32) ? 8 : (TW == 16 ? 16 : 8));
+  constexpr int TN = TILE_N / (TW * TH);
   static_assert(GROUPS == 1 || TW == 32, "pixel groups only exist for the first-layer geometry");
   const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
   const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
@@ -246,6 +264,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
       named_bar_sync(EPI_BAR_ID, EPI_THREADS);
     }
     mbar_wait_parked(tfull0 + 8u * acc, acc_phase);
+    if (leader) trace(p.tr, 7, tile);                     // epilogue: accumulator complete
     tc_fence_after();
     if (warp_active) {
 #pragma unroll 1
@@ -310,6 +329,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, h0 >> 1, n0);
         else tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0, h0, n0);
         tma_store_commit();
+        trace(p.tr, 8, tile);                             // epilogue: tile stored
       }
     }
   }
@@ -368,10 +388,12 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (threadIdx.x == 0) trace(p.tr, 1, 0);          // kernel entry (after barrier init / alloc issue)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (threadIdx.x == 0) trace(p.tr, 2, 0);          // setup done
 
   const int ksteps = 9 * p.kchunks;
 
@@ -389,6 +411,7 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
           const int tap = ks / p.kchunks, kc = ks % p.kchunks;
           const int r = tap / 3, s = tap % 3;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (ks == 0) trace(p.tr, 3, tile);                                 // producer: first load of a tile issued
           const uint32_t a_dst = smem_base + stage * SL::STAGE_BYTES;
           const uint32_t b_dst = a_dst + SL::A_BYTES;
           mbar_expect_tx(full_bar(stage), SL::STAGE_BYTES);
@@ -408,10 +431,12 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+        trace(p.tr, 4, tile);                             // MMA: accumulator available
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TILE_N);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full_bar(stage), phase);
+          if (ks == 0) trace(p.tr, 5, tile);              // MMA: first operands of the tile landed
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * SL::STAGE_BYTES;
           const uint32_t b_addr = a_addr + SL::A_BYTES;
@@ -427,11 +452,179 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));                      // accumulator complete
+        trace(p.tr, 6, tile);                             // MMA: all MMAs of the tile issued
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
     epilogue_role<TW, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
                                                                         smem_gen + SL::STG_OFFSET, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) trace(p.tr, 9, 0);          // teardown
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ K1 v2: halo-resident implicit GEMM
+// v1 re-fetches the pixel tile once per filter tap (9x the input bytes through L2 -> SMEM), which the timeline
+// trace showed to be the limiter (TMA supply, not the tensor pipe).  v2 loads each pixel tile ONCE per channel
+// chunk WITH its one-pixel halo -- a single 4-D TMA box {KC, 10, TH+2, TN} at (c0, w0-1, h0-1, n0), again using
+// the TMA zero fill for the SAME padding -- and feeds all nine taps from it: the B operand of tap (r,s) is the
+// same shared-memory tile viewed through a descriptor whose start address is shifted by (r*10 + s) pixel rows.
+// Tiles are 8 pixels wide so that the 8 rows of every UMMA core-matrix group are contiguous halo rows and the
+// group stride (SBO) is one halo row of 10 pixels; TH x 8 pixels per image, TN images per tile (TH*TN = 32),
+// one MMA of N = 8*TH per image.  Only the weights are streamed per tap (ring of A stages).
+template <int KC, int TH, bool POOL, bool OUT_F32>
+struct Smem2 {
+  static constexpr int TN = 32 / TH;
+  static constexpr int HALO_ROWS = TN * (TH + 2) * 10;
+  static constexpr int HALO_BYTES = (HALO_ROWS * KC + 1023) / 1024 * 1024;
+  static constexpr int HBUFS = 2;
+  static constexpr int A_BYTES = TILE_M * KC;
+  static constexpr int STG_BYTES = StageTile<POOL, OUT_F32>::BYTES;
+  static constexpr int BUDGET = 232448 - 1024 - 512 - STG_BYTES - HBUFS * HALO_BYTES;
+  static constexpr int ASTAGES = (BUDGET / A_BYTES) > 8 ? 8 : (BUDGET / A_BYTES);
+  static constexpr int HALO_OFFSET = 0;
+  static constexpr int A_OFFSET = HBUFS * HALO_BYTES;
+  static constexpr int STG_OFFSET = A_OFFSET + ASTAGES * A_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+  static_assert(ASTAGES >= 3, "not enough shared memory for the weight ring");
+};
+
+template <int KC, int TH, bool POOL, bool OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                      const __grid_constant__ CUtensorMap map_y, const TcParams p) {
+  using SL = Smem2<KC, TH, POOL, OUT_F32>;
+  constexpr int TN = SL::TN;
+  constexpr int AS = SL::ASTAGES, HB = SL::HBUFS;
+  constexpr int NIMG = 8 * TH;                        // MMA N = pixels of one image block
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + SL::BAR_OFFSET;
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (AS + s); };
+  auto hfull = [&](int b) { return bar_base + 8u * (2 * AS + b); };
+  auto hempty = [&](int b) { return bar_base + 8u * (2 * AS + HB + b); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * AS + 2 * HB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AS + 2 * HB + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * AS + 2 * HB + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SL::BAR_OFFSET + 8 * (2 * AS + 2 * HB + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_y);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < AS; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int b = 0; b < HB; ++b) { mbar_init(hfull(b), 1); mbar_init(hempty(b), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  auto decode = [&](int tile, int& mt, int& n0, int& h0, int& w0) {
+    mt = tile % p.m_tiles;
+    int pt = tile / p.m_tiles;
+    const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
+    const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
+    n0 = pt * TN; h0 = th_i * TH; w0 = tw_i * 8;
+  };
+
+  if (warp == 0) {
+    // ===================== halo producer: one box per (tile, channel chunk) =====================
+    if (lane == 0) {
+      int hb = 0; uint32_t hphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int mt, n0, h0, w0;
+        decode(tile, mt, n0, h0, w0);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(hempty(hb), hphase ^ 1u);
+          mbar_expect_tx(hfull(hb), SL::HALO_ROWS * KC);
+          tma_load_4d(smem_base + SL::HALO_OFFSET + hb * SL::HALO_BYTES, &map_x, hfull(hb), kc * KC, w0 - 1, h0 - 1, n0);
+          if (++hb == HB) { hb = 0; hphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== weight producer: one {KC, 128} box per (tile, chunk, tap) =====================
+    if (lane == 0) {
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(aempty(as), aphase ^ 1u);
+            mbar_expect_tx(afull(as), SL::A_BYTES);
+            tma_load_2d(smem_base + SL::A_OFFSET + as * SL::A_BYTES, &map_w, afull(as), tap * p.cin + kc * KC, mt * TILE_M);
+            if (++as == AS) { as = 0; aphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(TILE_M, NIMG, true, true);
+      // B view: rows of KC bytes, 8-row groups one halo row (10 pixels) apart
+      constexpr uint64_t b_hi = ((uint64_t)((10 * KC) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KC == 128 ? 2 : 4) << 61) | ((uint64_t)1 << 16);
+      int as = 0; uint32_t aphase = 0;
+      int hb = 0; uint32_t hphase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TILE_N);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(hfull(hb), hphase);
+          tc_fence_after();
+          const uint32_t halo = smem_base + SL::HALO_OFFSET + hb * SL::HALO_BYTES;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap - 3 * r;
+            mbar_wait(afull(as), aphase);
+            tc_fence_after();
+            const uint64_t a_desc = make_smem_desc<KC>(smem_base + SL::A_OFFSET + as * SL::A_BYTES);
+#pragma unroll
+            for (int n = 0; n < TN; ++n) {
+              const uint32_t b_addr = halo + (uint32_t)(((n * (TH + 2) + r) * 10 + s) * KC);
+              const uint64_t b_desc = b_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+#pragma unroll
+              for (int k = 0; k < KC / UMMA_K; ++k)
+                umma_i8(d_tmem + (uint32_t)(n * NIMG), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                        (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(aempty(as));
+            if (++as == AS) { as = 0; aphase ^= 1u; }
+          }
+          umma_commit(hempty(hb));                       // halo buffer free once these MMAs retire
+          if (++hb == HB) { hb = 0; hphase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
+    epilogue_role<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
+                                                                            smem_gen + SL::STG_OFFSET, warp, lane);
   }
 
   tc_fence_before();
@@ -749,6 +942,7 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
   // two pixel groups per tile when the accumulator lanes would otherwise be half empty
   const int G = (!f32 && d.cout == 64 && d.h % 16 == 0) ? 2 : 1;
   TcParams p;
+  p.tr = Trace{nullptr, 0};
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
   p.tiles_w = 1;
   p.tiles_h = d.h / (8 * G);
@@ -786,7 +980,102 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
   return go(conv3x3_u8c3_tc_kernel<false, false, 0, 1>, K5Smem<false, false, 1>::TOTAL);
 }
 
+// ---- v2 (halo-resident) launch
+template <int KC, int TH, bool POOL, bool OUT_F32>
+int launch_v2_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, cudaStream_t st) {
+  auto kern = conv3x3_i8_tc2_kernel<KC, TH, POOL, OUT_F32>;
+  constexpr int smem = Smem2<KC, TH, POOL, OUT_F32>::TOTAL;
+  static_assert(smem <= 232448, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, smem, st>>>(mw, mx, my, p);
+  QNNB_CUDA(cudaGetLastError());
+  return QNNB_OK;
+}
+
+template <int KC, int TH>
+int launch_v2_th(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, bool pool, bool f32, cudaStream_t st) {
+  if (f32) return launch_v2_variant<KC, TH, false, true>(mw, mx, my, p, grid, st);
+  if (pool) return launch_v2_variant<KC, TH, true, false>(mw, mx, my, p, grid, st);
+  return launch_v2_variant<KC, TH, false, false>(mw, mx, my, p, grid, st);
+}
+
+template <int KC>
+int launch_v2_kc(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, int th, bool pool, bool f32, cudaStream_t st) {
+  if (th == 32) return launch_v2_th<KC, 32>(mw, mx, my, p, grid, pool, f32, st);
+  if (th == 16) return launch_v2_th<KC, 16>(mw, mx, my, p, grid, pool, f32, st);
+  return launch_v2_th<KC, 8>(mw, mx, my, p, grid, pool, f32, st);
+}
+
+bool pick_geometry_v2(int h, int w, Geometry* g) {
+  if (w % 8 != 0) return false;
+  if (h % 32 == 0) { *g = {8, 32, 1}; return true; }
+  if (h % 16 == 0) { *g = {8, 16, 2}; return true; }
+  if (h % 8 == 0) { *g = {8, 8, 4}; return true; }
+  return false;
+}
+
+int launch_conv_tc_v2(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
+  Geometry g;
+  pick_geometry_v2(d.h, d.w, &g);
+  const int KC = (d.cin % 128 == 0) ? 128 : 64;
+  const CUtensorMapSwizzle swz = (KC == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const bool pool = d.epi.pool == 2;
+  const bool f32 = d.epi.act == QNNB_ACT_NONE;
+  CUtensorMap mw, mx, my;
+  memset(&my, 0, sizeof(my));
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * d.cin, (cuuint64_t)d.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * d.cin};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)TILE_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return QNNB_ECUDA; }
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+    cuuint64_t strides[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.w * d.cin, (cuuint64_t)d.h * d.w * d.cin};
+    cuuint32_t box[4] = {(cuuint32_t)KC, 10u, (cuuint32_t)(g.th + 2), (cuuint32_t)g.tn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(halo) failed with %d", (int)r); return QNNB_ECUDA; }
+  }
+  if (!f32) {
+    int rc = make_output_map(encode, &my, y, d.n, pool ? d.h / 2 : d.h, pool ? d.w / 2 : d.w, d.cout, TILE_M, g, pool);
+    if (rc) return rc;
+  }
+  TcParams p;
+  p.tr = g_trace;
+  p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
+  p.tiles_w = d.w / 8;
+  p.tiles_h = d.h / g.th;
+  p.tiles_n = ceil_div(d.n, g.tn);
+  p.m_tiles = d.cout / TILE_M;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.m_tiles;
+  p.kchunks = d.cin / KC;
+  p.out_pitch = TILE_M;
+  p.y = y;
+  p.epi = make_epi(d.epi);
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (KC == 128) return launch_v2_kc<128>(mw, mx, my, p, grid, g.th, pool, f32, st);
+  return launch_v2_kc<64>(mw, mx, my, p, grid, g.th, pool, f32, st);
+}
+
 }  // namespace
+
+void set_trace_buffer(unsigned long long* buf, int cap) { g_trace.buf = buf; g_trace.cap = cap; }
+
+bool conv_tc_v1_supported(const qnnb_conv_desc& d) {
+  Geometry g;
+  return d.in_kind == QNNB_KIND_I8 && pick_geometry(d.h, d.w, &g);
+}
 
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   Geometry g;
@@ -795,13 +1084,20 @@ bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   if (d.kh != 3 || d.kw != 3 || d.stride != 1) { *why = "only 3x3 stride 1"; return false; }
   if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
   if (d.cout % 128 != 0) { *why = "Cout must be a multiple of 128"; return false; }
-  if (!pick_geometry(d.h, d.w, &g)) { *why = "spatial size must be 32xH(H%8==0), 16x16k or 8x8"; return false; }
+  if (!pick_geometry_v2(d.h, d.w, &g)) { *why = "spatial size must be a multiple of 8 in both directions"; return false; }
   if (d.epi.act == QNNB_ACT_QUANT && !is_pow2_scale(d.epi.acc_scale)) { *why = "acc_scale must be a power of two"; return false; }
   return epilogue_ok(d, why);
 }
 
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
   if (first_layer_shape(d)) return launch_first_layer(d, x, w, y, st);
+  // Kernel choice (measured on B200, profiles/): the halo-resident kernel wins when a tile is one 32-row block
+  // (one N = 256 MMA per tap: 32-row maps, -8..-20 %); with 16- or 8-row maps it needs N = 128 / 64 MMAs that re-read
+  // the weight tile from shared memory per image and becomes SMEM-bandwidth bound, so v1 keeps those shapes.
+  Geometry g1;
+  const bool v1_ok = pick_geometry(d.h, d.w, &g1);
+  const bool want_v2 = (d.impl == QNNB_IMPL_TCGEN05_V1) ? false : (d.impl == QNNB_IMPL_TCGEN05 ? true : (d.h % 32 == 0 || !v1_ok));
+  if (want_v2 || !v1_ok) return launch_conv_tc_v2(d, x, w, y, st);
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
   Geometry g;
@@ -837,6 +1133,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   }
 
   TcParams p;
+  p.tr = g_trace;
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
   p.tiles_w = d.w / g.tw;
   p.tiles_h = d.h / g.th;

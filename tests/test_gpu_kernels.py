@@ -326,9 +326,21 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", TC_CASES, ids=["n%d_%dx%d_%d-%d_w%da%d%s%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_pool" if c[7] else "", "_f32" if c[8] else "") for c in TC_CASES])
-def test_conv2d_tcgen05_bit_exact(case):
+TC_CASES_V2_ONLY = [
+    (3, 24, 40, 64, 128, 4, 4, True, False),      # any multiple of 8: 24 rows -> 8-row blocks of 4 images, 5 column tiles
+    (2, 64, 16, 128, 128, 4, 4, False, False),    # tall map: two 32-row tiles per image
+    (5, 16, 16, 192, 256, 8, 8, True, False),     # Cin = 192 (three 64-byte chunks), ragged image pair
+    (1, 8, 8, 64, 128, 4, 4, False, True),        # raw accumulators, 8x8 (image group of 4 with 3 missing)
+]
+
+
+@pytest.mark.parametrize("impl", ["v2", "v1"])
+@pytest.mark.parametrize("case", TC_CASES + TC_CASES_V2_ONLY, ids=["n%d_%dx%d_%d-%d_w%da%d%s%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_pool" if c[7] else "", "_f32" if c[8] else "") for c in TC_CASES + TC_CASES_V2_ONLY])
+def test_conv2d_tcgen05_bit_exact(case, impl):
     q, L, K = _mods()
+    if impl == "v1" and case in TC_CASES_V2_ONLY:
+        pytest.skip("shape only covered by the halo-resident kernel")
+    IMPL = L.IMPL_TCGEN05 if impl == "v2" else L.IMPL_TCGEN05_V1
     n, h, w, cin, cout, nb, abits, pool, f32_out = case
     rng = np.random.default_rng(_seed(case))
     x, xs = _rand_input(rng, "i8", (n, h, w, cin), abits)
@@ -338,7 +350,7 @@ def test_conv2d_tcgen05_bit_exact(case):
     if f32_out:
         # scale 1, no bias / BN: the fp32 output IS the int32 accumulator (|acc| < 2^24 here)
         epi = K.make_epilogue(1.0, act=L.ACT_NONE)
-        y = K.conv2d(K.QTensor("i8", dev(x), xs, cin), wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05)
+        y = K.conv2d(K.QTensor("i8", dev(x), xs, cin), wp, 3, 3, cout, 1, epi, impl=IMPL)
         torch.cuda.synchronize()
         got = y.data.cpu().numpy()
         lv = exact.quantize_levels(kernel, nb)
@@ -356,7 +368,7 @@ def test_conv2d_tcgen05_bit_exact(case):
     i_, s_ = K.bn_constants(*bn, 1e-4)
     epi = K.make_epilogue(K.acc_scale(xs, 1.0 / (1 << (nb - 1))), bias=dev(bias), bn_inv=dev(i_), bn_shift=dev(s_),
                           act=L.ACT_QUANT, abits=abits, pool=2 if pool else 0)
-    y = K.conv2d(K.QTensor("i8", dev(x), xs, cin), wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05)
+    y = K.conv2d(K.QTensor("i8", dev(x), xs, cin), wp, 3, 3, cout, 1, epi, impl=IMPL)
     torch.cuda.synchronize()
     got = y.data.cpu().numpy().astype(np.int32)
     assert got.shape == want.shape
