@@ -108,6 +108,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -154,6 +155,22 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, int (&v)[64]) {
       : "memory");
 }
 
+// tcgen05.wait::ld that also "redefines" the 64 destination registers of an earlier tmem_ld64, so the compiler
+// cannot schedule any use of them above the wait (needed once loads are issued ahead of their use)
+__device__ __forceinline__ void tmem_ld_wait_dep(int (&v)[64]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+        "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+        "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+        "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]), "+r"(v[32]), "+r"(v[33]), "+r"(v[34]), "+r"(v[35]), "+r"(v[36]),
+        "+r"(v[37]), "+r"(v[38]), "+r"(v[39]), "+r"(v[40]), "+r"(v[41]), "+r"(v[42]), "+r"(v[43]), "+r"(v[44]), "+r"(v[45]),
+        "+r"(v[46]), "+r"(v[47]), "+r"(v[48]), "+r"(v[49]), "+r"(v[50]), "+r"(v[51]), "+r"(v[52]), "+r"(v[53]), "+r"(v[54]),
+        "+r"(v[55]), "+r"(v[56]), "+r"(v[57]), "+r"(v[58]), "+r"(v[59]), "+r"(v[60]), "+r"(v[61]), "+r"(v[62]), "+r"(v[63])
+      :
+      : "memory");
+}
+
 // UMMA shared-memory matrix descriptor, K-major operand whose rows are KC bytes wide and stored with the
 // KC-byte swizzle (KC = 64 or 128): 8-row groups are 8*KC bytes apart (SBO); LBO is unused for swizzled
 // K-major layouts (set to 16 B); version = 1 (Blackwell); layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
@@ -196,11 +213,22 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// compiled in only with -DQNNB_TRACE (make TRACE=1): even a never-taken branch in the single-thread MMA issue loop
+// costs measurable time (v1 16x16 layer: 22 -> 32 us)
 __device__ __forceinline__ void trace(const Trace& tr, int tag, int idx) {
+#ifdef QNNB_TRACE
+  // lock-free: every recording thread owns a 512-event region (chosen by its warp) and a private counter kept in
+  // the first word of that region; two fire-and-forget stores per event
   if (tr.buf != nullptr && blockIdx.x == 0) {
-    const unsigned long long slot = atomicAdd(tr.buf, 1ull);
-    if ((int)(2 * slot + 3) < tr.cap) { tr.buf[1 + 2 * slot] = ((unsigned long long)tag << 32) | (unsigned)idx; tr.buf[2 + 2 * slot] = gtime(); }
+    unsigned long long* reg = tr.buf + (threadIdx.x >> 5) * 1024;
+    const unsigned long long k = reg[0];
+    if (k < 510) {
+      reg[2 + 2 * k] = ((unsigned long long)tag << 32) | (unsigned)idx;
+      reg[3 + 2 * k] = gtime();
+      reg[0] = k + 1;
+    }
   }
+#endif
 }
 
 struct TcParams {
@@ -228,9 +256,22 @@ struct StageTile {
 // FOLD: acc_scale is a power of two (see QConst); PITCH: bytes per staged row (0 = runtime p.out_pitch).
 // GROUPS (K5 only, TW = 32): when Cout <= 64 the 128 TMEM lanes hold GROUPS = 2 pixel groups of 64 channels --
 // lane L is channel L % 64 of the pixels 8*(L / 64) rows further down, so one tile covers 16 image rows.
+// NSTG staging tiles (stg, stg + stg_bytes): with 2, the TMA store of tile t drains while tile t+1 is computed.
+// PREFETCH: issue both 64-column TMEM loads up front (128 accumulator registers; fine at 384 threads per CTA, too
+// many for the 512-thread first-layer kernel).
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1, int TH_ = 0, int NSTG = 1, bool PREFETCH = true>
+__device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
+                                                uint32_t tempty0, uint8_t* stg0, int stg_bytes, int warp, int lane);
+
 template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1, int TH_ = 0>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, uint8_t* stg, int warp, int lane) {
+  epilogue_role_n<TW, POOL, OUT_F32, FOLD, PITCH, GROUPS, TH_, 1>(p, map_y, tmem_base, tfull0, tempty0, stg, 0, warp, lane);
+}
+
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS, int TH_, int NSTG, bool PREFETCH>
+__device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
+                                                uint32_t tempty0, uint8_t* stg0, int stg_bytes, int warp, int lane) {
   constexpr int TH = TH_ ? TH_ : ((TW == 32) ? 8 : (TW == 16 ? 16 : 8));
   constexpr int TN = TILE_N / (TW * TH);
   static_assert(GROUPS == 1 || TW == 32, "pixel groups only exist for the first-layer geometry");
@@ -241,6 +282,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
   const int ch_in_tile = (GROUPS == 2) ? ((quarter & 1) * 32 + lane) : (quarter * 32 + lane);
   const bool leader = (warp == 4 && lane == 0);
   const Epi& e = p.epi;
+  int cur_mt = -1;
+  ChanConst cc = {};
+  QConst qc = {1.f, 0.f, 1.f, 0.f};
   int it = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     const int mt = tile % p.m_tiles;
@@ -251,69 +295,97 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
     const int ch = mt * TILE_M + ch_in_tile;
     const bool ch_ok = ch < p.cout;
     const bool warp_active = (mt * TILE_M + ch_in_tile - lane) < p.cout; // warp-uniform
-    const ChanConst cc = load_chan(e, ch, ch_ok);                 // fp32 output path
-    const QConst qc = make_qconst<FOLD>(e, ch, ch_ok);            // quantised output path
+    // per-channel constants: global loads, so only when the channel tile changes (with an even grid stride a
+    // persistent CTA keeps the same channel tile for its whole life)
+    if (mt != cur_mt) {
+      cur_mt = mt;
+      if constexpr (OUT_F32) cc = load_chan(e, ch, ch_ok);
+      else qc = make_qconst<FOLD>(e, ch, ch_ok);
+    }
     const bool dec = qc.b < 0.f;
     const int pitch = PITCH ? PITCH : p.out_pitch;
     const float qm = e.qm;
     const int acc = it & 1;
     const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-    if constexpr (!OUT_F32) {
-      // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
+    uint8_t* stg = stg0 + ((NSTG == 2) ? (it & 1) * stg_bytes : 0);
+    if (leader) trace(p.tr, 11, tile);                    // epilogue: loop top
+    if constexpr (!OUT_F32 && NSTG == 1) {
+      // single staging tile: the previous TMA store must have finished READING it before it is overwritten
       if (leader) tma_store_wait_read();
       named_bar_sync(EPI_BAR_ID, EPI_THREADS);
     }
     mbar_wait_parked(tfull0 + 8u * acc, acc_phase);
     if (leader) trace(p.tr, 7, tile);                     // epilogue: accumulator complete
     tc_fence_after();
-    if (warp_active) {
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const int col0 = half * 128 + j * 64;
-        int v[64];
-        __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
-        tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + col0), v);
-        tmem_ld_wait();
-        if (j == 1) {
-          // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+    // one 64-column chunk (rows [row0, row0 + 64/TW) of image n0 + img) -> output
+    auto process = [&](int (&v)[64], int col0) {
+      const int img = col0 / (TH * TW);
+      const int row0 = (col0 % (TH * TW)) / TW;
+      if constexpr (OUT_F32) {
+        const int nimg = n0 + img;
+        if (nimg >= p.n) return;                   // warp-uniform (ragged last image group)
+        constexpr int R = 64 / TW;
+        const long long pix0 = ((long long)nimg * p.h + (h0 + grow + row0)) * p.w + w0;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+          for (int c = 0; c < TW; ++c) {
+            const float z = affine((float)v[rr * TW + c], cc);
+            if (ch_ok) ((float*)p.y)[(pix0 + (long long)rr * p.w + c) * p.cout + ch] = z;
+          }
         }
-        // 64 columns = rows [row0, row0 + 64/TW) of image n0 + img
-        const int img = col0 / (TH * TW);
-        const int row0 = (col0 % (TH * TW)) / TW;
-        if constexpr (OUT_F32) {
-          const int nimg = n0 + img;
-          if (nimg >= p.n) continue;               // warp-uniform (ragged last image group)
-          constexpr int R = 64 / TW;
-          const long long pix0 = ((long long)nimg * p.h + (h0 + grow + row0)) * p.w + w0;
+      } else if constexpr (POOL) {
+        constexpr int PR = 64 / TW / 2, PC = TW / 2;
+        // every lane of an active warp owns a real channel (Cout % 32 == 0 on this path)
+        uint8_t* srow = stg + (img * (TH / 2) * PC + ((grow + row0) >> 1) * PC) * pitch + ch_in_tile;
 #pragma unroll
-          for (int rr = 0; rr < R; ++rr) {
+        for (int pr = 0; pr < PR; ++pr) {
 #pragma unroll
-            for (int c = 0; c < TW; ++c) {
-              const float z = affine((float)v[rr * TW + c], cc);
-              if (ch_ok) ((float*)p.y)[(pix0 + (long long)rr * p.w + c) * p.cout + ch] = z;
-            }
+          for (int pc = 0; pc < PC; ++pc) {
+            const int i00 = (2 * pr) * TW + 2 * pc;
+            const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
+            const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
+            srow[(pr * PC + pc) * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(dec ? mn : mx, qc), qm);
           }
-        } else if constexpr (POOL) {
-          constexpr int PR = 64 / TW / 2, PC = TW / 2;
-          // every lane of an active warp owns a real channel (Cout % 32 == 0 on this path)
-          uint8_t* srow = stg + (img * (TH / 2) * PC + ((grow + row0) >> 1) * PC) * pitch + ch_in_tile;
+        }
+      } else {
+        uint8_t* srow = stg + (grow * TW + col0) * pitch + ch_in_tile;
 #pragma unroll
-          for (int pr = 0; pr < PR; ++pr) {
-#pragma unroll
-            for (int pc = 0; pc < PC; ++pc) {
-              const int i00 = (2 * pr) * TW + 2 * pc;
-              const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
-              const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
-              srow[(pr * PC + pc) * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(dec ? mn : mx, qc), qm);
-            }
+        for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
+      }
+    };
+    if (warp_active) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + half * 128);
+      if constexpr (PREFETCH) {
+        int va[64], vb[64];
+        __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld64(taddr, va);
+        tmem_ld64(taddr + 64, vb);                 // second chunk in flight while the first is processed
+        tmem_ld_wait_dep(va);
+        if (leader) trace(p.tr, 12, tile);
+        process(va, half * 128);
+        __syncwarp();
+        tmem_ld_wait_dep(vb);
+        // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        if (leader) trace(p.tr, 13, tile);
+        process(vb, half * 128 + 64);
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          int v[64];
+          __syncwarp();
+          tmem_ld64(taddr + 64 * j, v);
+          tmem_ld_wait_dep(v);
+          if (leader) trace(p.tr, 12 + j, tile);
+          if (j == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
           }
-        } else {
-          uint8_t* srow = stg + (grow * TW + col0) * pitch + ch_in_tile;
-#pragma unroll
-          for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
+          process(v, half * 128 + 64 * j);
         }
       }
     } else {
@@ -322,8 +394,12 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
     }
+    if (leader) trace(p.tr, 14, tile);                    // epilogue: math done
     if constexpr (!OUT_F32) {
       fence_proxy_async();                         // staging writes -> visible to the TMA (async proxy)
+      // two staging tiles: the store issued one tile ago has had this whole tile to drain; once the leader has
+      // confirmed that, the barrier below also tells everyone that the OTHER tile may be overwritten next
+      if (NSTG == 2 && leader) tma_store_wait_read();
       named_bar_sync(EPI_BAR_ID, EPI_THREADS);
       if (leader) {
         if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, h0 >> 1, n0);
@@ -666,7 +742,7 @@ struct K5Smem {
   static constexpr int HALO_OFFSET = B_OFFSET + STAGES * B_BYTES;
   static constexpr int STG_OFFSET = (HALO_OFFSET + 2 * HALO_BYTES + 1023) / 1024 * 1024;
   static constexpr int STG_BYTES = OUT_F32 ? 0 : (POOL ? TILE_N * G / 4 : TILE_N * G) * (TILE_M / G);
-  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + 2 * STG_BYTES;          // two staging tiles (store of t overlaps t+1)
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
@@ -753,7 +829,9 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        trace(p.tr, 4, tile);
         mbar_wait(full_bar(stage), phase);
+        trace(p.tr, 5, tile);
         tc_fence_after();
         const uint64_t a_desc = make_smem_desc_interleaved(smem_base + SL::A_OFFSET + mt * (TILE_M * K5_KB * G), 128, SBO);
         const uint64_t b_desc = make_smem_desc_interleaved(smem_base + SL::B_OFFSET + stage * SL::B_BYTES, 128, SBO);
@@ -767,8 +845,8 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH, G>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
-                                                               sg + SL::STG_OFFSET, warp, lane);
+    epilogue_role_n<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH, G, 0, 2, false>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
+                                                                       sg + SL::STG_OFFSET, SL::STG_BYTES, warp, lane);
   } else if (warp >= 4 + NUM_EPI_WARPS) {
     // ===================== im2col producers (128 threads) =====================
     const int t = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
@@ -810,6 +888,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
         }
       }
       named_bar_sync(1, K5_PRODUCERS);
+      if (t == 0) trace(p.tr, 10, tile);             // producer: halo staged
       if (tile + (int)gridDim.x < p.num_tiles) issue_loads(tile + gridDim.x);      // prefetch the next tile's rows
       mbar_wait_parked(empty_bar(stage), phase ^ 1u);
       uint8_t* btile = sg + SL::B_OFFSET + stage * SL::B_BYTES;
@@ -833,6 +912,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
       }
       fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
       mbar_arrive(full_bar(stage));
+      if (t == 0) trace(p.tr, 3, tile);              // producer: im2col tile published
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   }
@@ -942,7 +1022,7 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
   // two pixel groups per tile when the accumulator lanes would otherwise be half empty
   const int G = (!f32 && d.cout == 64 && d.h % 16 == 0) ? 2 : 1;
   TcParams p;
-  p.tr = Trace{nullptr, 0};
+  p.tr = g_trace;
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
   p.tiles_w = 1;
   p.tiles_h = d.h / (8 * G);
