@@ -259,7 +259,10 @@ struct StageTile {
 // NSTG staging tiles (stg, stg + stg_bytes): with 2, the TMA store of tile t drains while tile t+1 is computed.
 // PREFETCH: issue both 64-column TMEM loads up front (128 accumulator registers; fine at 384 threads per CTA, too
 // many for the 512-thread first-layer kernel).
-template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1, int TH_ = 0, int NSTG = 1, bool PREFETCH = true>
+// ILV (v2 kernel, TW = 8): the accumulator columns are ordered [row][image][8 px] (image-interleaved rows) instead of
+// [image][row][8 px]; the output tensor map has its N and H dimensions swapped to match.
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1, int TH_ = 0, int NSTG = 1, bool PREFETCH = true,
+          bool ILV = false>
 __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                                 uint32_t tempty0, uint8_t* stg0, int stg_bytes, int warp, int lane);
 
@@ -269,7 +272,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
   epilogue_role_n<TW, POOL, OUT_F32, FOLD, PITCH, GROUPS, TH_, 1>(p, map_y, tmem_base, tfull0, tempty0, stg, 0, warp, lane);
 }
 
-template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS, int TH_, int NSTG, bool PREFETCH>
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS, int TH_, int NSTG, bool PREFETCH, bool ILV>
 __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                                 uint32_t tempty0, uint8_t* stg0, int stg_bytes, int warp, int lane) {
   constexpr int TH = TH_ ? TH_ : ((TW == 32) ? 8 : (TW == 16 ? 16 : 8));
@@ -319,6 +322,48 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
     tc_fence_after();
     // one 64-column chunk (rows [row0, row0 + 64/TW) of image n0 + img) -> output
     auto process = [&](int (&v)[64], int col0) {
+      if constexpr (ILV) {
+        // 64 columns = 8 groups of 8 pixels; group g = row (g / TN) of image (g % TN)
+        static_assert(!ILV || TW == 8, "interleaved order is defined for 8-pixel-wide tiles");
+        constexpr int RPC = 8 / TN;                  // image rows covered by one chunk
+        const int row0 = (col0 >> 3) / TN;
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int gi = 0; gi < 8; ++gi) {
+            const int hh = row0 + gi / TN, img = gi % TN;
+            if (n0 + img < p.n) {
+              const long long pix0 = ((long long)(n0 + img) * p.h + (h0 + hh)) * p.w + w0;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float z = affine((float)v[gi * 8 + c], cc);
+                if (ch_ok) ((float*)p.y)[(pix0 + c) * p.cout + ch] = z;
+              }
+            }
+          }
+        } else if constexpr (POOL) {
+          constexpr int PRC = RPC / 2;
+          uint8_t* srow = stg + ((row0 >> 1) * TN * 4) * pitch + ch_in_tile;
+#pragma unroll
+          for (int pr = 0; pr < PRC; ++pr) {
+#pragma unroll
+            for (int img = 0; img < TN; ++img) {
+#pragma unroll
+              for (int pc = 0; pc < 4; ++pc) {
+                const int i00 = ((2 * pr) * TN + img) * 8 + 2 * pc;
+                constexpr int VS = TN * 8;             // columns between vertically adjacent pixels
+                const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + VS], v[i00 + VS + 1]));
+                const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + VS], v[i00 + VS + 1]));
+                srow[((pr * TN + img) * 4 + pc) * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(dec ? mn : mx, qc), qm);
+              }
+            }
+          }
+        } else {
+          uint8_t* srow = stg + col0 * pitch + ch_in_tile;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
+        }
+        return;
+      }
       const int img = col0 / (TH * TW);
       const int row0 = (col0 % (TH * TW)) / TW;
       if constexpr (OUT_F32) {
@@ -402,7 +447,10 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
       if (NSTG == 2 && leader) tma_store_wait_read();
       named_bar_sync(EPI_BAR_ID, EPI_THREADS);
       if (leader) {
-        if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, h0 >> 1, n0);
+        if constexpr (ILV) {                       // output map dimensions are (C, W, N, H)
+          if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, n0, h0 >> 1);
+          else tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0, n0, h0);
+        } else if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, h0 >> 1, n0);
         else tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0, h0, n0);
         tma_store_commit();
         trace(p.tr, 8, tile);                             // epilogue: tile stored
@@ -552,8 +600,12 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // the TMA zero fill for the SAME padding -- and feeds all nine taps from it: the B operand of tap (r,s) is the
 // same shared-memory tile viewed through a descriptor whose start address is shifted by (r*10 + s) pixel rows.
 // Tiles are 8 pixels wide so that the 8 rows of every UMMA core-matrix group are contiguous halo rows and the
-// group stride (SBO) is one halo row of 10 pixels; TH x 8 pixels per image, TN images per tile (TH*TN = 32),
-// one MMA of N = 8*TH per image.  Only the weights are streamed per tap (ring of A stages).
+// group stride (SBO) is one halo row of 10 pixels; TH x 8 pixels per image, TN images per tile (TH*TN = 32).
+// The halo tile is stored [row][image][10 px] (the tensor map lists N before H), so that the 8-row groups of ALL
+// TN images are uniformly strided and one N = 256 MMA per tap covers the whole tile (per-image N = 64/128 MMAs
+// re-read the weight tile from shared memory and were SMEM-bandwidth bound).  Accumulator columns and the
+// staged output are therefore in [row][image][px] order; the output tensor map is permuted the same way.
+// Only the weights are streamed per tap (ring of A stages).
 template <int KC, int TH, bool POOL, bool OUT_F32>
 struct Smem2 {
   static constexpr int TN = 32 / TH;
@@ -579,7 +631,6 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   using SL = Smem2<KC, TH, POOL, OUT_F32>;
   constexpr int TN = SL::TN;
   constexpr int AS = SL::ASTAGES, HB = SL::HBUFS;
-  constexpr int NIMG = 8 * TH;                        // MMA N = pixels of one image block
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -635,7 +686,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(hempty(hb), hphase ^ 1u);
           mbar_expect_tx(hfull(hb), SL::HALO_ROWS * KC);
-          tma_load_4d(smem_base + SL::HALO_OFFSET + hb * SL::HALO_BYTES, &map_x, hfull(hb), kc * KC, w0 - 1, h0 - 1, n0);
+          tma_load_4d(smem_base + SL::HALO_OFFSET + hb * SL::HALO_BYTES, &map_x, hfull(hb), kc * KC, w0 - 1, n0, h0 - 1);
           if (++hb == HB) { hb = 0; hphase ^= 1u; }
         }
       }
@@ -659,7 +710,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_i8(TILE_M, NIMG, true, true);
+      constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, true, true);
       // B view: rows of KC bytes, 8-row groups one halo row (10 pixels) apart
       constexpr uint64_t b_hi = ((uint64_t)((10 * KC) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KC == 128 ? 2 : 4) << 61) | ((uint64_t)1 << 16);
       int as = 0; uint32_t aphase = 0;
@@ -680,15 +731,12 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             mbar_wait(afull(as), aphase);
             tc_fence_after();
             const uint64_t a_desc = make_smem_desc<KC>(smem_base + SL::A_OFFSET + as * SL::A_BYTES);
+            // halo row (h + r) of every image starts r*TN halo rows further down; pixel shift s within the row
+            const uint32_t b_addr = halo + (uint32_t)((r * TN * 10 + s) * KC);
+            const uint64_t b_desc = b_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
 #pragma unroll
-            for (int n = 0; n < TN; ++n) {
-              const uint32_t b_addr = halo + (uint32_t)(((n * (TH + 2) + r) * 10 + s) * KC);
-              const uint64_t b_desc = b_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
-#pragma unroll
-              for (int k = 0; k < KC / UMMA_K; ++k)
-                umma_i8(d_tmem + (uint32_t)(n * NIMG), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                        (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < KC / UMMA_K; ++k)
+              umma_i8(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
             umma_commit(aempty(as));
             if (++as == AS) { as = 0; aphase ^= 1u; }
           }
@@ -699,8 +747,8 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
-                                                                            smem_gen + SL::STG_OFFSET, warp, lane);
+    epilogue_role_n<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH, 1, true, /*ILV*/ true>(
+        p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), smem_gen + SL::STG_OFFSET, 0, warp, lane);
   }
 
   tc_fence_before();
@@ -1119,17 +1167,24 @@ int launch_conv_tc_v2(const qnnb_conv_desc& d, const void* x, const void* w, voi
     if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return QNNB_ECUDA; }
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
-    cuuint64_t strides[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.w * d.cin, (cuuint64_t)d.h * d.w * d.cin};
-    cuuint32_t box[4] = {(cuuint32_t)KC, 10u, (cuuint32_t)(g.th + 2), (cuuint32_t)g.tn};
+    // dimension order (C, W, N, H): the box lands as [row][image][10 px][KC]
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.n, (cuuint64_t)d.h};
+    cuuint64_t strides[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.h * d.w * d.cin, (cuuint64_t)d.w * d.cin};
+    cuuint32_t box[4] = {(cuuint32_t)KC, 10u, (cuuint32_t)g.tn, (cuuint32_t)(g.th + 2)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(halo) failed with %d", (int)r); return QNNB_ECUDA; }
   }
   if (!f32) {
-    int rc = make_output_map(encode, &my, y, d.n, pool ? d.h / 2 : d.h, pool ? d.w / 2 : d.w, d.cout, TILE_M, g, pool);
-    if (rc) return rc;
+    const int oh = pool ? d.h / 2 : d.h, ow = pool ? d.w / 2 : d.w;
+    cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)ow, (cuuint64_t)d.n, (cuuint64_t)oh};
+    cuuint64_t strides[3] = {(cuuint64_t)d.cout, (cuuint64_t)oh * ow * d.cout, (cuuint64_t)ow * d.cout};
+    cuuint32_t box[4] = {(cuuint32_t)TILE_M, (cuuint32_t)(pool ? 4 : 8), (cuuint32_t)g.tn, (cuuint32_t)(pool ? g.th / 2 : g.th)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&my, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(output) failed with %d", (int)r); return QNNB_ECUDA; }
   }
   TcParams p;
   p.tr = g_trace;
@@ -1176,7 +1231,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   // the weight tile from shared memory per image and becomes SMEM-bandwidth bound, so v1 keeps those shapes.
   Geometry g1;
   const bool v1_ok = pick_geometry(d.h, d.w, &g1);
-  const bool want_v2 = (d.impl == QNNB_IMPL_TCGEN05_V1) ? false : (d.impl == QNNB_IMPL_TCGEN05 ? true : (d.h % 32 == 0 || !v1_ok));
+  const bool want_v2 = (d.impl != QNNB_IMPL_TCGEN05_V1);
   if (want_v2 || !v1_ok) return launch_conv_tc_v2(d, x, w, y, st);
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
