@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqnnb200.so")
+# QNNB_LIB selects an alternative build of the same library (kernel A/B experiments); never a different backend
+LIB_PATH = os.environ.get("QNNB_LIB") or os.path.join(_HERE, "libqnnb200.so")
 
 # ---- constants mirrored from include/qnnb200.h
 KIND_NONE, KIND_U8, KIND_I8, KIND_B1, KIND_F32 = -1, 0, 1, 2, 3

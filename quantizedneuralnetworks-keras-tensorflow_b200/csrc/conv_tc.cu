@@ -82,6 +82,14 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
     if (++spins > (1u << 22)) __trap();
   }
 }
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -644,6 +652,9 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AS + 2 * HB + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * AS + 2 * HB + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SL::BAR_OFFSET + 8 * (2 * AS + 2 * HB + 4));
+  // weight stages made ready so far (monotonic): written by the watcher thread, polled by the MMA issuer
+  const uint32_t a_ready = tmem_slot + 8u;
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_gen + SL::BAR_OFFSET + 8 * (2 * AS + 2 * HB + 4) + 8) = 0u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -707,28 +718,60 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         }
       }
     }
+#ifndef QNNB_NO_WATCHER
+  } else if (warp == 2) {
+    // ===================== weight-stage watcher =====================
+    // An mbarrier try_wait costs the waiting thread ~180 cycles even when the phase is already complete, and the
+    // tcgen05.mma issue is itself blocking, so nine such waits per chunk in the MMA issuer left the tensor pipe idle
+    // ~30 % of the time (cycle accounting, profiles/).  This otherwise idle thread absorbs the waits and publishes a
+    // running count of landed weight stages; the issuer only polls that word (one shared-memory load).
+    if (lane == 0) {
+      int as = 0; uint32_t aphase = 0, count = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < 9 * p.kchunks; ++ks) {
+          mbar_wait(afull(as), aphase);
+          st_release_shared(a_ready, ++count);
+          if (++as == AS) { as = 0; aphase ^= 1u; }
+        }
+      }
+    }
+#endif
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, true, true);
+      uint32_t a_need = 0, a_seen = 0;
+      (void)a_need; (void)a_seen;
       // B view: rows of KC bytes, 8-row groups one halo row (10 pixels) apart
       constexpr uint64_t b_hi = ((uint64_t)((10 * KC) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KC == 128 ? 2 : 4) << 61) | ((uint64_t)1 << 16);
       int as = 0; uint32_t aphase = 0;
       int hb = 0; uint32_t hphase = 0;
       int it = 0;
+#ifdef QNNB_TRACE
+      // cycle accounting of this thread (TRACE builds): where does the issue loop wait?
+      long long c_tempty = 0, c_hfull = 0, c_afull = 0, c_t0 = clock64();
+#define QNNB_CLK(var, stmt) { long long c0__ = clock64(); stmt; var += clock64() - c0__; }
+#else
+#define QNNB_CLK(var, stmt) { stmt; }
+#endif
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        QNNB_CLK(c_tempty, mbar_wait(tempty_bar(acc), acc_phase ^ 1u));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TILE_N);
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(hfull(hb), hphase);
+          QNNB_CLK(c_hfull, mbar_wait(hfull(hb), hphase));
           tc_fence_after();
           const uint32_t halo = smem_base + SL::HALO_OFFSET + hb * SL::HALO_BYTES;
           for (int tap = 0; tap < 9; ++tap) {
             const int r = tap / 3, s = tap - 3 * r;
-            mbar_wait(afull(as), aphase);
+#ifndef QNNB_NO_WATCHER
+            ++a_need;
+            QNNB_CLK(c_afull, { uint32_t spins = 0; while ((int)(a_seen - a_need) < 0) { a_seen = ld_acquire_shared(a_ready); if (++spins > (1u << 26)) __trap(); } });
+#else
+            QNNB_CLK(c_afull, mbar_wait(afull(as), aphase));
+#endif
             tc_fence_after();
             const uint64_t a_desc = make_smem_desc<KC>(smem_base + SL::A_OFFSET + as * SL::A_BYTES);
             // halo row (h + r) of every image starts r*TN halo rows further down; pixel shift s within the row
@@ -745,6 +788,13 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         }
         umma_commit(tfull_bar(acc));
       }
+#ifdef QNNB_TRACE
+      if (p.tr.buf != nullptr && blockIdx.x == 0) {
+        unsigned long long* o = p.tr.buf + 15 * 1024;
+        o[0] = 5; o[2] = (unsigned long long)c_tempty; o[3] = (unsigned long long)c_hfull; o[4] = (unsigned long long)c_afull;
+        o[5] = 0; o[6] = (unsigned long long)(clock64() - c_t0); o[7] = (unsigned long long)it;
+      }
+#endif
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
     epilogue_role_n<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH, 1, true, /*ILV*/ true>(

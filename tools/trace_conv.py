@@ -29,8 +29,11 @@ e1.record()
 torch.cuda.synchronize()
 L.check(L.lib().qnnb_debug_set_trace(None, 0))
 b = buf.cpu().numpy()
+acct = b[15 * 1024:15 * 1024 + 8]
+if acct[0] == 5:
+    print("MMA thread cycles: wait tempty %d, wait hfull %d, wait afull %d, issue %d, total %d over %d tiles" % tuple(int(v) for v in acct[2:8]))
 ev = []
-for wp_ in range(16):
+for wp_ in range(15):
     reg = b[wp_ * 1024:(wp_ + 1) * 1024]
     for i in range(int(reg[0])):
         ev.append((int(reg[3 + 2 * i]), int(reg[2 + 2 * i]) >> 32, int(reg[2 + 2 * i]) & 0xffffffff, wp_))
