@@ -56,6 +56,8 @@ extern "C" {
 #define QNNB_ACT_QUANT  1      /* quantized_tanh(., abits) -> int8 levels   (quantized_ops.py:87-100) */
 #define QNNB_ACT_SIGN   2      /* binary_tanh -> packed bits (+1 <=> z > 2^-24) (binary_ops.py:37-51) */
 #define QNNB_ACT_LEAKY  3      /* LeakyReLU(alpha) fp32 out                  (model_factory.py:27,34) */
+#define QNNB_ACT_SIGN_I8 4     /* binary_tanh -> int8 levels +1 / -1 (same decision as QNNB_ACT_SIGN): the layout that lets the
+                                  next BinaryConv2D run on the int8 tensor cores (binary_ops.py:37-51) */
 
 /* kernel selection (testing / profiling) */
 #define QNNB_IMPL_AUTO    0
@@ -132,10 +134,14 @@ int64_t qnnb_packed_weight_bytes(int32_t wfmt, int32_t kh, int32_t kw, int32_t c
  * layers that follow it in models/vgg.py / models/resnet.py fused into the epilogue.
  *   x : in_kind U8/I8 -> bytes [n][h][w][cin]; B1 -> uint32 [n][h][w][ceil(cin/32)]; F32 -> float
  *   w : packed by qnnb_pack_weights (QNNB_WFMT_B1 iff in_kind == B1)
- *   y : act QUANT -> int8 [n][oh][ow][cout]; SIGN -> uint32 [n][oh][ow][ceil(cout/32)];
+ *   y : act QUANT / SIGN_I8 -> int8 [n][oh][ow][cout]; SIGN -> uint32 [n][oh][ow][ceil(cout/32)];
  *       NONE/LEAKY -> float [n][oh][ow][cout]; (oh,ow) after the optional pool.
  */
 int qnnb_conv2d(const qnnb_conv_desc* desc, const void* x, const void* w, void* y, void* stream);
+
+/* 1 when qnnb_conv2d would run this descriptor on the tcgen05 tensor-core kernels (QNNB_IMPL_AUTO), else 0; the
+ * host uses it to choose between the bit-packed (QNNB_ACT_SIGN) and the int8 (QNNB_ACT_SIGN_I8) form of a +-1 map. */
+int qnnb_conv2d_tc_supported(const qnnb_conv_desc* desc);
 
 /* output spatial size of qnnb_conv2d (after pooling) */
 int qnnb_conv2d_out_shape(const qnnb_conv_desc* desc, int32_t* oh, int32_t* ow);

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("QNNB_LIB") or os.path.join(_HERE, "libqnnb200.so")
 KIND_NONE, KIND_U8, KIND_I8, KIND_B1, KIND_F32 = -1, 0, 1, 2, 3
 W_QUANT, W_BINARY, W_TERNARY = 0, 1, 2
 WFMT_I8, WFMT_B1 = 0, 1
-ACT_NONE, ACT_QUANT, ACT_SIGN, ACT_LEAKY = 0, 1, 2, 3
+ACT_NONE, ACT_QUANT, ACT_SIGN, ACT_LEAKY, ACT_SIGN_I8 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_GENERIC, IMPL_TCGEN05, IMPL_TCGEN05_V1 = 0, 1, 2, 3
 EINVAL, ECUDA, EUNSUPPORTED = -1, -2, -3
 
@@ -68,6 +68,7 @@ PROTOTYPES = {
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_packed_weight_bytes": (C.c_int64, [C.c_int32] * 5),
     "qnnb_conv2d": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qnnb_conv2d_tc_supported": (C.c_int, [C.POINTER(ConvDesc)]),
     "qnnb_conv2d_out_shape": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qnnb_dense": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_quantize_act": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),

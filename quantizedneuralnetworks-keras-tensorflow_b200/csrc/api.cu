@@ -21,7 +21,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int validate_epilogue(const qnnb_epilogue& e, bool allow_pool, bool allow_residual) {
-  QNNB_CHECK_ARG(e.act >= QNNB_ACT_NONE && e.act <= QNNB_ACT_LEAKY, "epilogue: bad act %d", e.act);
+  QNNB_CHECK_ARG(e.act >= QNNB_ACT_NONE && e.act <= QNNB_ACT_SIGN_I8, "epilogue: bad act %d", e.act);
   QNNB_CHECK_ARG(e.act != QNNB_ACT_QUANT || (e.abits >= 2 && e.abits <= 8), "epilogue: abits=%d outside 2..8", e.abits);
   QNNB_CHECK_ARG((e.bn_inv == nullptr) == (e.bn_shift == nullptr), "epilogue: bn_inv and bn_shift must come together");
   QNNB_CHECK_ARG(e.pool == 0 || (allow_pool && e.pool == 2), "epilogue: pool=%d not supported here", e.pool);
@@ -82,6 +82,12 @@ int64_t qnnb_packed_weight_bytes(int32_t wfmt, int32_t kh, int32_t kw, int32_t c
 int qnnb_pack_weights(int32_t mode, int32_t nb, float H, const float* w_hwio, int32_t kh, int32_t kw, int32_t cin,
                       int32_t cout, int32_t wfmt, void* out, float* scratch, void* stream) {
   return launch_pack_weights(mode, nb, H, w_hwio, kh, kw, cin, cout, wfmt, out, scratch, (cudaStream_t)stream);
+}
+
+int qnnb_conv2d_tc_supported(const qnnb_conv_desc* d) {
+  if (!d || validate_conv(*d) != QNNB_OK) return 0;
+  const char* why = "";
+  return conv_tc_supported(*d, &why) ? 1 : 0;
 }
 
 int qnnb_conv2d_out_shape(const qnnb_conv_desc* d, int32_t* oh, int32_t* ow) {

@@ -160,9 +160,13 @@ __device__ __forceinline__ float qaffine(int acc, const QConst& q) {
   return __fadd_rn(f, q.c);                     // == z * qm
 }
 
-// clamp bounds are integers, so clamping before the round-to-nearest-even conversion is identical to after
+// clamp bounds are integers, so clamping before the round-to-nearest-even conversion is identical to after.
+// The conversion itself is one RN add of 1.5 * 2^23: for |v| <= 2^22 the sum's ulp is 1, so the add rounds v to the
+// nearest integer (ties to even, the magic constant being even) and leaves it, in two's complement, in the low
+// mantissa bits -- same result as cvt.rni.s32.f32 but on the FMA pipe instead of the quarter-rate conversion unit.
+// Only the LOW BYTE of the returned word is the level (callers store it as int8).
 __device__ __forceinline__ int quant_scaled(float zq, float qm) {
-  return __float2int_rn(fminf(fmaxf(zq, -qm), qm - 1.f));
+  return __float_as_int(__fadd_rn(fminf(fmaxf(zq, -qm), qm - 1.f), 12582912.f));
 }
 
 __device__ __forceinline__ float act_leaky(float z, float alpha) { return z > 0.f ? z : __fmul_rn(alpha, z); }

@@ -221,10 +221,13 @@ conv_generic_kernel(const ConvP p) {
       }
       z[j] = v;
     }
-    if (e.act == QNNB_ACT_QUANT) {
+    if (e.act == QNNB_ACT_QUANT || e.act == QNNB_ACT_SIGN_I8) {
       uint32_t packed = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) packed |= ((uint32_t)(act_quant(z[j], e.qm) & 0xff)) << (8 * j);
+      for (int j = 0; j < 4; ++j) {
+        const int lvl = (e.act == QNNB_ACT_QUANT) ? act_quant(z[j], e.qm) : (act_sign(z[j]) ? 1 : -1);
+        packed |= ((uint32_t)(lvl & 0xff)) << (8 * j);
+      }
       if (pvalid) {
         int8_t* dst = (int8_t*)p.y + opix * p.cout + ch0;
         if ((p.cout & 3) == 0) { if (ch0 < p.cout) *reinterpret_cast<uint32_t*>(dst) = packed; }

@@ -249,7 +249,13 @@ struct TcParams {
   Epi epi;
 };
 
-constexpr int EPI_BAR_ID = 2;
+// two decoupled epilogue warp groups (see epilogue_role_n) where a second staging tile fits; -DQNNB_NO_SPLIT for A/B runs
+#ifdef QNNB_NO_SPLIT
+constexpr bool SPLIT_EPILOGUE = false;
+#else
+constexpr bool SPLIT_EPILOGUE = true;
+#endif
+constexpr int EPI_BAR_ID = 2;                      // named barriers 2 and 3
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 
 template <bool POOL, bool OUT_F32>
@@ -269,8 +275,13 @@ struct StageTile {
 // many for the 512-thread first-layer kernel).
 // ILV (v2 kernel, TW = 8): the accumulator columns are ordered [row][image][8 px] (image-interleaved rows) instead of
 // [image][row][8 px]; the output tensor map has its N and H dimensions swapped to match.
+// SPLIT: the eight warps form two independent groups of four (one warp per TMEM lane quarter); group g owns
+// accumulator g, i.e. every second tile of the CTA, drains all 256 columns of it and has its own staging tile, named
+// barrier and TMA-store leader.  The two groups run out of phase, so the TMEM-load latency, barrier and store of one
+// tile overlap the arithmetic of the next (lock-step, every tile pays them in sequence).  tempty barriers then count 4.
+// SIGN: the activation is binary_tanh instead of quantized_tanh (level +1 / -1; qm is 1, so qaffine yields z itself).
 template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS = 1, int TH_ = 0, int NSTG = 1, bool PREFETCH = true,
-          bool ILV = false>
+          bool ILV = false, bool SIGN = false, bool SPLIT = false>
 __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                                 uint32_t tempty0, uint8_t* stg0, int stg_bytes, int warp, int lane);
 
@@ -280,24 +291,35 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
   epilogue_role_n<TW, POOL, OUT_F32, FOLD, PITCH, GROUPS, TH_, 1>(p, map_y, tmem_base, tfull0, tempty0, stg, 0, warp, lane);
 }
 
-template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS, int TH_, int NSTG, bool PREFETCH, bool ILV>
+template <bool SIGN>
+__device__ __forceinline__ int out_level(float zq, float qm) {
+  if constexpr (SIGN) return act_sign(zq) ? 1 : -1;
+  else return quant_scaled(zq, qm);
+}
+
+template <int TW, bool POOL, bool OUT_F32, bool FOLD, int PITCH, int GROUPS, int TH_, int NSTG, bool PREFETCH, bool ILV, bool SIGN, bool SPLIT>
 __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtensorMap* map_y, uint32_t tmem_base, uint32_t tfull0,
                                                 uint32_t tempty0, uint8_t* stg0, int stg_bytes, int warp, int lane) {
   constexpr int TH = TH_ ? TH_ : ((TW == 32) ? 8 : (TW == 16 ? 16 : 8));
   constexpr int TN = TILE_N / (TW * TH);
   static_assert(GROUPS == 1 || TW == 32, "pixel groups only exist for the first-layer geometry");
   const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 (hardware restriction: warp_id % 4)
-  const int half = (warp - 4) >> 2;             // which 128 columns of the accumulator
+  const int egrp = (warp - 4) >> 2;             // epilogue warp group
+  const int half = SPLIT ? 0 : egrp;            // lock-step: which 128 columns of the accumulator
   const int group = (GROUPS == 2) ? (quarter >> 1) : 0;
   const int grow = group * TH;                  // row offset of this lane's pixel group inside the tile
   const int ch_in_tile = (GROUPS == 2) ? ((quarter & 1) * 32 + lane) : (quarter * 32 + lane);
-  const bool leader = (warp == 4 && lane == 0);
+  const bool leader = SPLIT ? (quarter == 0 && lane == 0) : (warp == 4 && lane == 0);
+  const int bar_id = SPLIT ? EPI_BAR_ID + egrp : EPI_BAR_ID;
+  constexpr int BAR_THREADS = SPLIT ? EPI_THREADS / 2 : EPI_THREADS;
+  constexpr int IT_STEP = SPLIT ? 2 : 1;
+  static_assert(!SPLIT || OUT_F32 || NSTG == 2, "split epilogue groups need one staging tile each");
   const Epi& e = p.epi;
   int cur_mt = -1;
   ChanConst cc = {};
   QConst qc = {1.f, 0.f, 1.f, 0.f};
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+  int it = SPLIT ? egrp : 0;
+  for (int tile = blockIdx.x + it * (int)gridDim.x; tile < p.num_tiles; tile += IT_STEP * (int)gridDim.x, it += IT_STEP) {
     const int mt = tile % p.m_tiles;
     int pt = tile / p.m_tiles;
     const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
@@ -313,17 +335,27 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
       if constexpr (OUT_F32) cc = load_chan(e, ch, ch_ok);
       else qc = make_qconst<FOLD>(e, ch, ch_ok);
     }
+    // Pooling picks max(acc) where the channel's map is increasing and min(acc) where it is decreasing (BN slope
+    // < 0).  min(x) = -max(-x), so instead of computing both extrema and selecting (5 ALU-pipe ops per output) the
+    // raw accumulators are multiplied by sg = +-1 (IMAD: FMA pipe) before ONE max reduction, and the sign is undone
+    // exactly inside the constants: negation commutes with every RN op.  qp = constants for the pooled path.
     const bool dec = qc.b < 0.f;
+    const int sg = dec ? -1 : 1;
+    QConst qp = qc;
+    if (dec) {
+      if constexpr (FOLD) { qp.a = -qc.a; qp.b = -qc.b; }     // ((sg*f + sg*a) * (sg*b)) + c
+      else qp.s = -qc.s;                                        // (sg*f) * (sg*s)
+    }
     const int pitch = PITCH ? PITCH : p.out_pitch;
     const float qm = e.qm;
     const int acc = it & 1;
     const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
     uint8_t* stg = stg0 + ((NSTG == 2) ? (it & 1) * stg_bytes : 0);
     if (leader) trace(p.tr, 11, tile);                    // epilogue: loop top
-    if constexpr (!OUT_F32 && NSTG == 1) {
-      // single staging tile: the previous TMA store must have finished READING it before it is overwritten
+    if constexpr (!OUT_F32 && (NSTG == 1 || SPLIT)) {
+      // single staging tile (per group): the previous TMA store must have finished READING it before it is overwritten
       if (leader) tma_store_wait_read();
-      named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+      named_bar_sync(bar_id, BAR_THREADS);
     }
     mbar_wait_parked(tfull0 + 8u * acc, acc_phase);
     if (leader) trace(p.tr, 7, tile);                     // epilogue: accumulator complete
@@ -359,16 +391,15 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
               for (int pc = 0; pc < 4; ++pc) {
                 const int i00 = ((2 * pr) * TN + img) * 8 + 2 * pc;
                 constexpr int VS = TN * 8;             // columns between vertically adjacent pixels
-                const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + VS], v[i00 + VS + 1]));
-                const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + VS], v[i00 + VS + 1]));
-                srow[((pr * TN + img) * 4 + pc) * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(dec ? mn : mx, qc), qm);
+                const int mx = max(max(v[i00] * sg, v[i00 + 1] * sg), max(v[i00 + VS] * sg, v[i00 + VS + 1] * sg));
+                srow[((pr * TN + img) * 4 + pc) * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qp), qm);
               }
             }
           }
         } else {
           uint8_t* srow = stg + col0 * pitch + ch_in_tile;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
+          for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(v[c], qc), qm);
         }
         return;
       }
@@ -396,20 +427,56 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
 #pragma unroll
           for (int pc = 0; pc < PC; ++pc) {
             const int i00 = (2 * pr) * TW + 2 * pc;
-            const int mx = max(max(v[i00], v[i00 + 1]), max(v[i00 + TW], v[i00 + TW + 1]));
-            const int mn = min(min(v[i00], v[i00 + 1]), min(v[i00 + TW], v[i00 + TW + 1]));
-            srow[(pr * PC + pc) * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(dec ? mn : mx, qc), qm);
+            const int mx = max(max(v[i00] * sg, v[i00 + 1] * sg), max(v[i00 + TW] * sg, v[i00 + TW + 1] * sg));
+            srow[(pr * PC + pc) * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qp), qm);
           }
         }
       } else {
         uint8_t* srow = stg + (grow * TW + col0) * pitch + ch_in_tile;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)quant_scaled(qaffine<FOLD>(v[c], qc), qm);
+        for (int c = 0; c < 64; ++c) srow[c * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(v[c], qc), qm);
       }
     };
     if (warp_active) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TILE_N + half * 128);
-      if constexpr (PREFETCH) {
+      if constexpr (SPLIT && PREFETCH) {
+        // four 64-column chunks, software pipelined: the load of chunk j+1 is issued after the wait for chunk j
+        // (tcgen05.wait::ld covers every load issued so far) and is in flight while chunk j is processed
+        int va[64], vb[64];
+        __syncwarp();
+        tmem_ld64(taddr, va);
+        tmem_ld_wait_dep(va);
+        __syncwarp();
+        tmem_ld64(taddr + 64, vb);
+        process(va, 0);
+        tmem_ld_wait_dep(vb);
+        __syncwarp();
+        tmem_ld64(taddr + 128, va);
+        process(vb, 64);
+        tmem_ld_wait_dep(va);
+        __syncwarp();
+        tmem_ld64(taddr + 192, vb);
+        process(va, 128);
+        tmem_ld_wait_dep(vb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        process(vb, 192);
+      } else if constexpr (SPLIT) {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          int v[64];
+          __syncwarp();
+          tmem_ld64(taddr + 64 * j, v);
+          tmem_ld_wait_dep(v);
+          if (j == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+          }
+          process(v, 64 * j);
+        }
+      } else if constexpr (PREFETCH) {
         int va[64], vb[64];
         __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld64(taddr, va);
@@ -452,8 +519,8 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
       fence_proxy_async();                         // staging writes -> visible to the TMA (async proxy)
       // two staging tiles: the store issued one tile ago has had this whole tile to drain; once the leader has
       // confirmed that, the barrier below also tells everyone that the OTHER tile may be overwritten next
-      if (NSTG == 2 && leader) tma_store_wait_read();
-      named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+      if (NSTG == 2 && !SPLIT && leader) tma_store_wait_read();
+      named_bar_sync(bar_id, BAR_THREADS);
       if (leader) {
         if constexpr (ILV) {                       // output map dimensions are (C, W, N, H)
           if constexpr (POOL) tma_store_4d(map_y, smem_u32(stg), mt * TILE_M, w0 >> 1, n0, h0 >> 1);
@@ -622,17 +689,21 @@ struct Smem2 {
   static constexpr int HBUFS = 2;
   static constexpr int A_BYTES = TILE_M * KC;
   static constexpr int STG_BYTES = StageTile<POOL, OUT_F32>::BYTES;
-  static constexpr int BUDGET = 232448 - 1024 - 512 - STG_BYTES - HBUFS * HALO_BYTES;
+  // pooled tiles stage 8 KB, so a second tile (one per epilogue group) is affordable; un-pooled ones (32 KB) keep the
+  // weight ring deep instead and run the epilogue in lock-step
+  static constexpr bool SPLIT = SPLIT_EPILOGUE && POOL && !OUT_F32;
+  static constexpr int NSTG = SPLIT ? 2 : 1;
+  static constexpr int BUDGET = 232448 - 1024 - 512 - NSTG * STG_BYTES - HBUFS * HALO_BYTES;
   static constexpr int ASTAGES = (BUDGET / A_BYTES) > 8 ? 8 : (BUDGET / A_BYTES);
   static constexpr int HALO_OFFSET = 0;
   static constexpr int A_OFFSET = HBUFS * HALO_BYTES;
   static constexpr int STG_OFFSET = A_OFFSET + ASTAGES * A_BYTES;
-  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + NSTG * STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
   static_assert(ASTAGES >= 3, "not enough shared memory for the weight ring");
 };
 
-template <int KC, int TH, bool POOL, bool OUT_F32>
+template <int KC, int TH, bool POOL, bool OUT_F32, bool SIGN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_y, const TcParams p) {
@@ -667,7 +738,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int b = 0; b < HB; ++b) { mbar_init(hfull(b), 1); mbar_init(hempty(b), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), SL::SPLIT ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -797,8 +868,8 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #endif
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role_n<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH, 1, true, /*ILV*/ true>(
-        p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), smem_gen + SL::STG_OFFSET, 0, warp, lane);
+    epilogue_role_n<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH, SL::NSTG, true, /*ILV*/ true, SIGN, SL::SPLIT>(
+        p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), smem_gen + SL::STG_OFFSET, SL::STG_BYTES, warp, lane);
   }
 
   tc_fence_before();
@@ -844,13 +915,14 @@ struct K5Smem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <bool POOL, bool OUT_F32, int PITCH, int G>
+template <bool POOL, bool OUT_F32, int PITCH, int G, bool SIGN = false>
 __global__ void __launch_bounds__(K5_THREADS, 1)
 conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const __grid_constant__ CUtensorMap map_y,
                        const TcParams p) {
   constexpr int TW = 32, TH = 8;
   using SL = K5Smem<POOL, OUT_F32, G>;
   constexpr int STAGES = SL::STAGES;
+  constexpr bool SPLIT = SPLIT_EPILOGUE && !OUT_F32;   // two staging tiles exist: one per epilogue group
   constexpr uint32_t SBO = 4 * G * 128;              // bytes between 8-row groups (4G K chunks of 128 B)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -903,7 +975,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCERS); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), SPLIT ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -943,7 +1015,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role_n<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH, G, 0, 2, false>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
+    epilogue_role_n<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH, G, 0, 2, false, false, SIGN, SPLIT>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
                                                                        sg + SL::STG_OFFSET, SL::STG_BYTES, warp, lane);
   } else if (warp >= 4 + NUM_EPI_WARPS) {
     // ===================== im2col producers (128 threads) =====================
@@ -1101,9 +1173,9 @@ int launch_kc(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& m
 
 bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
   if (d.epi.res_kind != QNNB_KIND_NONE) { *why = "residual epilogue not on the tensor-core path"; return false; }
-  if (d.epi.act == QNNB_ACT_QUANT) return true;
+  if (d.epi.act == QNNB_ACT_QUANT || d.epi.act == QNNB_ACT_SIGN_I8) return true;
   if (d.epi.act == QNNB_ACT_NONE && d.epi.pool == 0) return true;
-  *why = "epilogue must be quantized_tanh (optionally pooled) or plain fp32";
+  *why = "epilogue must be quantized_tanh / binary_tanh to int8 levels (optionally pooled) or plain fp32";
   return false;
 }
 
@@ -1146,6 +1218,18 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
     return QNNB_OK;
   };
   if (f32) return go(conv3x3_u8c3_tc_kernel<false, true, 0, 1>, K5Smem<false, true, 1>::TOTAL);
+  if (d.epi.act == QNNB_ACT_SIGN_I8) {
+    if (G == 2) {
+      if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64, 2, true>, K5Smem<true, false, 2>::TOTAL);
+      return go(conv3x3_u8c3_tc_kernel<false, false, 64, 2, true>, K5Smem<false, false, 2>::TOTAL);
+    }
+    if (p.out_pitch == 128) {
+      if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 128, 1, true>, K5Smem<true, false, 1>::TOTAL);
+      return go(conv3x3_u8c3_tc_kernel<false, false, 128, 1, true>, K5Smem<false, false, 1>::TOTAL);
+    }
+    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 0, 1, true>, K5Smem<true, false, 1>::TOTAL);
+    return go(conv3x3_u8c3_tc_kernel<false, false, 0, 1, true>, K5Smem<false, false, 1>::TOTAL);
+  }
   if (G == 2) {
     if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64, 2>, K5Smem<true, false, 2>::TOTAL);
     return go(conv3x3_u8c3_tc_kernel<false, false, 64, 2>, K5Smem<false, false, 2>::TOTAL);
@@ -1159,9 +1243,9 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
 }
 
 // ---- v2 (halo-resident) launch
-template <int KC, int TH, bool POOL, bool OUT_F32>
+template <int KC, int TH, bool POOL, bool OUT_F32, bool SIGN = false>
 int launch_v2_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, cudaStream_t st) {
-  auto kern = conv3x3_i8_tc2_kernel<KC, TH, POOL, OUT_F32>;
+  auto kern = conv3x3_i8_tc2_kernel<KC, TH, POOL, OUT_F32, SIGN>;
   constexpr int smem = Smem2<KC, TH, POOL, OUT_F32>::TOTAL;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
@@ -1177,6 +1261,10 @@ int launch_v2_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtens
 template <int KC, int TH>
 int launch_v2_th(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, bool pool, bool f32, cudaStream_t st) {
   if (f32) return launch_v2_variant<KC, TH, false, true>(mw, mx, my, p, grid, st);
+  if (p.epi.act == QNNB_ACT_SIGN_I8) {
+    if (pool) return launch_v2_variant<KC, TH, true, false, true>(mw, mx, my, p, grid, st);
+    return launch_v2_variant<KC, TH, false, false, true>(mw, mx, my, p, grid, st);
+  }
   if (pool) return launch_v2_variant<KC, TH, true, false>(mw, mx, my, p, grid, st);
   return launch_v2_variant<KC, TH, false, false>(mw, mx, my, p, grid, st);
 }
@@ -1259,7 +1347,7 @@ void set_trace_buffer(unsigned long long* buf, int cap) { g_trace.buf = buf; g_t
 
 bool conv_tc_v1_supported(const qnnb_conv_desc& d) {
   Geometry g;
-  return d.in_kind == QNNB_KIND_I8 && pick_geometry(d.h, d.w, &g);
+  return d.in_kind == QNNB_KIND_I8 && d.epi.act != QNNB_ACT_SIGN_I8 && pick_geometry(d.h, d.w, &g);
 }
 
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
@@ -1270,7 +1358,7 @@ bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
   if (d.cout % 128 != 0) { *why = "Cout must be a multiple of 128"; return false; }
   if (!pick_geometry_v2(d.h, d.w, &g)) { *why = "spatial size must be a multiple of 8 in both directions"; return false; }
-  if (d.epi.act == QNNB_ACT_QUANT && !is_pow2_scale(d.epi.acc_scale)) { *why = "acc_scale must be a power of two"; return false; }
+  if ((d.epi.act == QNNB_ACT_QUANT || d.epi.act == QNNB_ACT_SIGN_I8) && !is_pow2_scale(d.epi.acc_scale)) { *why = "acc_scale must be a power of two"; return false; }
   return epilogue_ok(d, why);
 }
 

@@ -100,38 +100,76 @@ dense_kernel(const DenseP p) {
 }
 
 // Fast path (int8 / bit-packed inputs, units <= 16, K a multiple of 16 bytes): the packed kernel is staged
-// once per CTA into shared memory and every lane streams 16-byte vectors of its image (512 B per warp
-// per step, fully coalesced), so HBM traffic is exactly one read of x.
+// once per CTA into shared memory by ONE bulk-async copy (cp.async.bulk + mbarrier) while every lane already has
+// its first XB 16-byte vectors of the image in flight (512 B per warp per load, fully coalesced), so the kernel
+// pays one memory latency, and HBM traffic is exactly one read of x.
+__device__ __forceinline__ uint32_t dsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 dense_smem_kernel(const DenseP p) {
-  extern __shared__ uint4 swv[];
+  extern __shared__ __align__(128) uint4 swv[];
+  __shared__ __align__(8) uint64_t wbar;
   const int kvec = p.kwords >> 2;
-  const uint4* wg = reinterpret_cast<const uint4*>(p.w);
-  for (int i = threadIdx.x; i < p.units * kvec; i += 256) swv[i] = __ldg(wg + i);
+  const uint32_t bar = dsmem_u32(&wbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(p.units * kvec) * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    constexpr uint32_t CH = 16384;
+    for (uint32_t off = 0; off < bytes; off += CH) {
+      const uint32_t sz = bytes - off < CH ? bytes - off : CH;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dsmem_u32(swv) + off), "l"((const char*)p.w + off), "r"(sz), "r"(bar) : "memory");
+    }
+  }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const bool active = lane < p.units;
   const ChanConst cc = load_chan(p.epi, lane, active);
+  constexpr int XB = 8;
+  bool weights_ready = false;
   for (int img = blockIdx.x * 8 + warp; img < p.n; img += gridDim.x * 8) {
     int acc[UG];
 #pragma unroll
     for (int u = 0; u < UG; ++u) acc[u] = 0;
     const uint4* xr = reinterpret_cast<const uint4*>(p.x) + (long long)img * kvec;
-    for (int kv = lane; kv < kvec; kv += 32) {
-      const uint4 xv = __ldg(xr + kv);
+    for (int kv0 = lane; kv0 < kvec; kv0 += 32 * XB) {
+      uint4 xb[XB];
 #pragma unroll
-      for (int u = 0; u < UG; ++u) {
-        if (u < p.units) {
-          const uint4 wv = swv[u * kvec + kv];
-          if constexpr (KIND == QNNB_KIND_B1) {
-            acc[u] += __popc(xv.x ^ wv.x) + __popc(xv.y ^ wv.y) + __popc(xv.z ^ wv.z) + __popc(xv.w ^ wv.w);
-          } else {
-            acc[u] = __dp4a((int)xv.x, (int)wv.x, acc[u]);
-            acc[u] = __dp4a((int)xv.y, (int)wv.y, acc[u]);
-            acc[u] = __dp4a((int)xv.z, (int)wv.z, acc[u]);
-            acc[u] = __dp4a((int)xv.w, (int)wv.w, acc[u]);
+      for (int j = 0; j < XB; ++j) {
+        const int kv = kv0 + 32 * j;
+        xb[j] = (kv < kvec) ? __ldg(xr + kv) : make_uint4(0, 0, 0, 0);
+      }
+      if (!weights_ready) {                      // warp-uniform: first pass only
+        uint32_t done = 0;
+        while (!done)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        weights_ready = true;
+      }
+#pragma unroll
+      for (int j = 0; j < XB; ++j) {
+        const int kv = kv0 + 32 * j;
+        if (kv < kvec) {
+          const uint4 xv = xb[j];
+#pragma unroll
+          for (int u = 0; u < UG; ++u) {
+            if (u < p.units) {
+              const uint4 wv = swv[u * kvec + kv];
+              if constexpr (KIND == QNNB_KIND_B1) {
+                acc[u] += __popc(xv.x ^ wv.x) + __popc(xv.y ^ wv.y) + __popc(xv.z ^ wv.z) + __popc(xv.w ^ wv.w);
+              } else {
+                acc[u] = __dp4a((int)xv.x, (int)wv.x, acc[u]);
+                acc[u] = __dp4a((int)xv.y, (int)wv.y, acc[u]);
+                acc[u] = __dp4a((int)xv.z, (int)wv.z, acc[u]);
+                acc[u] = __dp4a((int)xv.w, (int)wv.w, acc[u]);
+              }
+            }
           }
         }
       }

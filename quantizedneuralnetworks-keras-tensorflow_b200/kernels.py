@@ -111,8 +111,7 @@ def acc_scale(x_scale: float, w_scale: float) -> np.float32:
 
 
 # --------------------------------------------------------------------------- conv / dense
-def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epilogue, impl=L.IMPL_AUTO,
-           out: torch.Tensor | None = None) -> QTensor:
+def _conv_desc(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, impl) -> L.ConvDesc:
     n, h, w, cin = (int(v) for v in x.shape)
     d = L.ConvDesc()
     d.n, d.h, d.w, d.cin = n, h, w, cin
@@ -120,6 +119,22 @@ def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epil
     d.in_kind = KIND_CODE[x.kind]
     d.impl = int(impl)
     d.epi = epi
+    return d
+
+
+def conv2d_on_tensor_cores(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, impl=L.IMPL_AUTO) -> bool:
+    """Would ``conv2d`` run this call on the tcgen05 kernels?  (The plan asks before choosing the int8 form of a
+    +-1 activation map over the bit-packed one.)"""
+    if impl == L.IMPL_GENERIC:
+        return False
+    d = _conv_desc(x, kh, kw, cout, stride, epi, impl)
+    return bool(L.lib().qnnb_conv2d_tc_supported(C.byref(d)))
+
+
+def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epilogue, impl=L.IMPL_AUTO,
+           out: torch.Tensor | None = None) -> QTensor:
+    n, h, w, cin = (int(v) for v in x.shape)
+    d = _conv_desc(x, kh, kw, cout, stride, epi, impl)
     oh, ow = C.c_int32(), C.c_int32()
     L.check(L.lib().qnnb_conv2d_out_shape(C.byref(d), C.byref(oh), C.byref(ow)))
     oh, ow = oh.value, ow.value
@@ -128,6 +143,8 @@ def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epil
         shape, dtype, kind, scale = (n, oh, ow, cout), torch.int8, "i8", 1.0 / float(1 << (epi.abits - 1))
     elif epi.act == L.ACT_SIGN:
         shape, dtype, kind, scale = (n, oh, ow, (cout + 31) // 32), torch.int32, "b1", 1.0
+    elif epi.act == L.ACT_SIGN_I8:
+        shape, dtype, kind, scale = (n, oh, ow, cout), torch.int8, "i8", 1.0          # levels +1 / -1
     else:
         shape, dtype, kind, scale = (n, oh, ow, cout), torch.float32, "f32", 1.0
     if out is None:

@@ -191,8 +191,16 @@ class Plan:
                 act = L.ACT_SIGN
             elif st.act[0] == "leaky":
                 act, alpha = L.ACT_LEAKY, float(st.act[1])
-        epi = K.make_epilogue(scale, bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift, residual=res,
-                              res_mul=st.res_mul, act=act, abits=abits, leaky_alpha=alpha, pool=2 if st.pool else 0)
+        kw = dict(bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift, residual=res, res_mul=st.res_mul, abits=abits,
+                  leaky_alpha=alpha, pool=2 if st.pool else 0)
+        epi = K.make_epilogue(scale, act=act, **kw)
+        if act == L.ACT_SIGN:
+            # A +-1 map has two storage forms: bit-packed words (XNOR/popc kernels) or int8 levels.  When this layer
+            # itself runs on the int8 tensor cores its output stays int8, so the next binary layer does too (measured:
+            # tcgen05 kind::i8 on +-1 levels beats the CUDA-core XNOR-popc kernel by >10x, profiles/).
+            epi8 = K.make_epilogue(scale, act=L.ACT_SIGN_I8, **kw)
+            if K.conv2d_on_tensor_cores(x, lay.kernel_size[0], lay.kernel_size[1], lay.filters, lay.strides[0], epi8, self.impl):
+                epi = epi8
         env[st.out] = K.conv2d(x, lay.packed_kernel(dev, wfmt), lay.kernel_size[0], lay.kernel_size[1], lay.filters,
                                lay.strides[0], epi, impl=self.impl)
         self.launches += 1

@@ -421,3 +421,55 @@ def test_first_layer_tcgen05_bit_exact(case):
     assert got.shape == want.shape
     bad = np.argwhere(got != want)
     assert bad.shape[0] == 0, "level mismatches: %d of %d, first %s" % (bad.shape[0], want.size, bad[:8].tolist())
+
+
+# --------------------------------------------------------------------------- +-1 maps as int8 levels (QNNB_ACT_SIGN_I8)
+SIGN_I8_CASES = [
+    # in_kind, n, h, w, cin, cout, pool, impl
+    ("u8", 3, 32, 32, 3, 64, True, "tc"),         # cfg2 layer 1 on the first-layer tcgen05 kernel (two pixel groups)
+    ("u8", 2, 32, 32, 3, 128, False, "tc"),
+    ("u8", 2, 32, 32, 3, 32, True, "tc"),         # runtime row pitch
+    ("i8", 3, 16, 16, 64, 128, True, "tc"),       # cfg2 layer 2: +-1 x +-1 on tcgen05 kind::i8
+    ("i8", 5, 8, 8, 128, 256, True, "tc"),        # cfg2 layer 3
+    ("i8", 2, 32, 32, 256, 128, False, "tc"),
+    ("i8", 2, 12, 10, 40, 70, False, "generic"),  # any shape on the CUDA-core kernel
+    ("i8", 2, 16, 16, 64, 128, True, "generic"),
+]
+
+
+@pytest.mark.parametrize("case", SIGN_I8_CASES, ids=["%s_n%d_%dx%d_%d-%d%s_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], "_pool" if c[6] else "", c[7]) for c in SIGN_I8_CASES])
+def test_conv2d_sign_to_int8_levels_bit_exact(case):
+    """BinaryConv2D + BN + binary_tanh (+ pool) with the +-1 result stored as int8 levels: same decisions as the
+    bit-packed form (oracle), on the tcgen05 kernels and on the generic kernel."""
+    q, L, K = _mods()
+    kind, n, h, w, cin, cout, pool, impl = case
+    rng = np.random.default_rng(_seed(("sign8",) + case))
+    if kind == "u8":
+        x, xs = _rand_input(rng, "u8", (n, h, w, cin))
+    else:
+        x, xs = _rand_input(rng, "b1", (n, h, w, cin))          # int8 +-1 levels, scale 1
+    kernel = rng.uniform(-1, 1, size=(3, 3, cin, cout)).astype(F32)
+    fan = 9 * cin
+    bias = rng.uniform(-0.3, 0.3, size=cout).astype(F32)
+    var_scale = fan * (0.11 if kind == "u8" else 1.0)
+    bn = (rng.uniform(0.3, 0.9, cout).astype(F32) * rng.choice([1, 1, -1], cout).astype(F32),
+          rng.uniform(-0.2, 0.2, cout).astype(F32),
+          (rng.uniform(-0.2, 0.2, cout) * np.sqrt(var_scale)).astype(F32),
+          (rng.uniform(0.5, 1.5, cout) * var_scale).astype(F32))
+    want, _ = oracle_layer(x, kind if kind == "u8" else "b1", xs, kernel, "binary", 1, 1.0, 1, bias=bias, bn=bn, eps=1e-4,
+                           act="binary", abits=4, pool=pool)
+    wp = K.pack_weights(dev(kernel), L.W_BINARY, 1, 1.0, L.WFMT_I8)
+    i_, s_ = K.bn_constants(*bn, 1e-4)
+    epi = K.make_epilogue(K.acc_scale(xs, 1.0), bias=dev(bias), bn_inv=dev(i_), bn_shift=dev(s_), act=L.ACT_SIGN_I8,
+                          pool=2 if pool else 0)
+    xq = K.QTensor(kind, dev(x), xs, cin)
+    IMPL = L.IMPL_TCGEN05 if impl == "tc" else L.IMPL_GENERIC
+    assert K.conv2d_on_tensor_cores(xq, 3, 3, cout, 1, epi, IMPL) == (impl == "tc")
+    y = K.conv2d(xq, wp, 3, 3, cout, 1, epi, impl=IMPL)
+    torch.cuda.synchronize()
+    assert y.kind == "i8" and y.scale == 1.0
+    got = y.data.cpu().numpy().astype(np.int32)
+    assert got.shape == want.shape
+    assert set(np.unique(got)) <= {-1, 1}
+    bad = np.argwhere(got != want.astype(np.int32))
+    assert bad.shape[0] == 0, "sign mismatches: %d of %d, first %s" % (bad.shape[0], want.size, bad[:8].tolist())
