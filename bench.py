@@ -27,6 +27,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "images/sec CIFAR-10 VGG full-qnn w4a4 inference (whole job)"
+
+
+def metric_name(workload):
+    # the headline metric is quoted on cfg3 (BASELINE.json configs[2]); other workloads say so in the metric string
+    return METRIC if workload == "cfg3" else "images/sec %s inference (whole job)" % workload
+
 WORKLOADS = {
     # name -> (config kwargs, batch per GPU)
     "cfg3": (dict(network_type='full-qnn', wbits=4, abits=4, architecture='VGG', nla=1, nfa=64, nlb=1, nfb=128, nlc=1, nfc=256), 1024),
@@ -34,6 +40,9 @@ WORKLOADS = {
     "cfg2": (dict(network_type='full-bnn', architecture='VGG', nla=1, nfa=64, nlb=1, nfb=128, nlc=1, nfc=256), 256),
     "cfg1": (dict(network_type='full-qnn', wbits=2, abits=2, architecture='VGG', dataset='MNIST', dim=28, channels=1,
                   nla=1, nfa=64, nlb=1, nfb=64, nlc=1, nfc=64), 100),
+    # BASELINE.json configs[4]: ResNet-(6n+2), n = 10, w4 kernels with fp32 LeakyReLU activations, and its ternary twin
+    "cfg5": (dict(network_type='qnn', wbits=4, abits=4, architecture='RESNET', nres=10), 1024),
+    "cfg5t": (dict(network_type='tnn', wbits=4, abits=4, architecture='RESNET', nres=10), 1024),
 }
 
 
@@ -86,6 +95,63 @@ def layer_work(cf, batch):
     feat = h * h * cin
     out.append(("dense", 2 * batch * feat * cf.classes, batch * feat + batch * cf.classes * 4 + feat * cf.classes))
     return out
+
+
+KIND_BYTES = {"u8": 1.0, "i8": 1.0, "b1": 1.0 / 8.0, "f32": 4.0}
+
+
+def plan_work(plan, env):
+    """Same accounting as layer_work but read off the executed plan (any architecture): per fused step
+    (name, ops, bytes) with ops = 2*MACs and bytes = input + residual + output tensors at their stored width + packed
+    kernel."""
+    out = []
+    ci = di = 0
+    for st in plan.steps:
+        if st.kind == "conv":
+            lay = st.layer
+            x, y = env[st.src], env[st.out]
+            n, h, w, cin = x.shape
+            _, oh, ow, cout = y.shape
+            ph, pw = (2 * oh, 2 * ow) if st.pool else (oh, ow)
+            macs = n * ph * pw * lay.kernel_size[0] * lay.kernel_size[1] * cin * cout
+            byts = n * h * w * cin * KIND_BYTES[x.kind] + n * oh * ow * cout * KIND_BYTES[y.kind] + lay.kernel.size
+            if st.res is not None:
+                r = env[st.res]
+                byts += float(np.prod(r.shape)) * KIND_BYTES[r.kind]
+            out.append(("conv%d" % ci, 2 * macs, byts))
+            ci += 1
+        elif st.kind == "dense":
+            x, _, _ = plan._resolve_dense_input(st.src, env)
+            n = int(x.shape[0])
+            fin = int(np.prod(x.shape[1:]))
+            units = st.layer.units
+            out.append(("dense%s" % ("" if di == 0 else di), 2 * n * fin * units, n * fin * KIND_BYTES[x.kind] + n * units * 4 + fin * units))
+            di += 1
+        else:
+            t = env[st.out]
+            out.append((st.layer.name, 0, 2 * float(np.prod(t.shape)) * KIND_BYTES[t.kind]))
+    return out
+
+
+def ncu_traffic(workload, step_index, n_steps):
+    """DRAM bytes per launch (read + write) of the step_index-th kernel of one forward, from the committed
+    Nsight Compute summary of this workload (profiles/r1_ncu_<workload>.csv, one row per launch of one forward)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_ncu_%s.csv" % workload)
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, body = rows[0], rows[1:]
+    if len(body) != n_steps:
+        return None
+    def col(prefix):
+        for i, h in enumerate(hdr):
+            if h.startswith(prefix):
+                unit = h[h.index("[") + 1:h.index("]")] if "[" in h else "byte"
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+                return float(body[step_index][i] or 0) * mult
+        return 0.0
+    return col("dram_read") + col("dram_write")
 
 
 # ------------------------------------------------------------------------------ clocks sampler
@@ -172,10 +238,10 @@ def run_reference(args):
         refstate.forward(nodes, x, trick=True)
     dt = time.perf_counter() - t0
     rate = sample * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: CIFAR-10 VGG %s w%da%d, reference CPU forward" % (args.workload, cf.network_type, cf.wbits, cf.abits),
+            "config": {"workload": "%s: %s %s %s w%da%d, reference CPU forward" % (args.workload, cf.dataset, cf.architecture, cf.network_type, cf.wbits, cf.abits),
                        "sample_images_per_step": sample},
             "cpu_baseline": {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d images per step (oracle O2a: torch-CPU fp32 restatement of the reference graph)" % sample},
@@ -237,7 +303,7 @@ def run_ours(args):
     # ---- CUDA graphs: one per input buffer.  Consecutive steps are independent batches, so they are replayed
     # round-robin on NS streams (graph i always on stream i % NS, with that stream's private memory pool): the
     # tail of one batch overlaps the head of the next, as in a serving loop.
-    NS = args.streams if args.streams > 0 else (1 if args.workload == "cfg4" else 4)
+    NS = args.streams if args.streams > 0 else (1 if args.workload in ("cfg4", "cfg5", "cfg5t") else 4)
     # world > 1: the per-step NCCL logit gather is issued eagerly from ONE dedicated communication stream, in step
     # order on every rank (a communicator must see the same sequence everywhere); forward graphs keep overlapping.
     comm = torch.cuda.Stream() if world > 1 else None
@@ -319,13 +385,13 @@ def run_ours(args):
     value = batch * world * args.steps / (ms * 1e-3)
 
     # ---- per-kernel timing (CUDA events between launches, same rotating inputs) for the roofline
-    work = layer_work(cf, batch)
+    envs = [plan.run(bufs[i]) for i in range(2)]
+    work = plan_work(plan, envs[0])
     # Each kernel is replayed REPS times from its own CUDA graph (no host launch gaps) on the activations
     # the previous layer produced, alternating between two independent forward environments.
     per = np.zeros(len(plan.steps))
     from qnn_b200 import kernels as K
     REPS = 10
-    envs = [plan.run(bufs[i]) for i in range(2)]
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
     for si, st in enumerate(plan.steps):
@@ -335,7 +401,7 @@ def run_ours(args):
             with torch.cuda.graph(g, stream=side):
                 for r in range(REPS):
                     env = dict(envs[r % 2])
-                    (plan._run_conv if st.kind == "conv" else plan._run_dense)(st, env)
+                    plan.run_step(st, env)
         torch.cuda.current_stream().wait_stream(side)
         g.replay()
         torch.cuda.synchronize()
@@ -356,11 +422,13 @@ def run_ours(args):
     if tensor_bound:
         achieved = ops / (per[dom] * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s", "frac": achieved / i8_peak,
-                "traffic": None, "kernel": name, "kernel_ms": float(per[dom]), "peak_source": i8_src}
+                "traffic": ncu_traffic(args.workload, dom, len(plan.steps)), "kernel": name, "kernel_ms": float(per[dom]), "peak_source": i8_src}
     else:
         achieved = byts / (per[dom] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": None, "kernel": name, "kernel_ms": float(per[dom]), "peak_source": pk["source"] + " copy bandwidth"}
+                "traffic": ncu_traffic(args.workload, dom, len(plan.steps)), "kernel": name, "kernel_ms": float(per[dom]),
+                "peak_source": pk["source"] + " copy bandwidth"}
+    roof["algorithmic"] = {"ops_per_launch": float(ops), "bytes_per_launch": float(byts)}
     roof["per_kernel_ms"] = {w[0]: float(p) for w, p in zip(work, per)}
 
     # ---- end to end through the public API: pinned host batch -> H2D -> fused plan (CUDA graph) -> D2H logits,
@@ -393,11 +461,13 @@ def run_ours(args):
             rate, cores = cpu_reference_rate(nodes, cf, sample)
             cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "%d images, median of 3 (oracle O2a: torch-CPU fp32 restatement of the reference graph)" % sample}
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": metric_name(args.workload), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8 (int32 accumulate, fp32 epilogue)", "data": "synthetic",
-                "config": {"workload": "%s: CIFAR-10 VGG %s w%da%d %d/%d/%d x %d/%d/%d, batch %d per GPU" % (
-                               args.workload, cf.network_type, cf.wbits, cf.abits, cf.nla, cf.nlb, cf.nlc, cf.nfa, cf.nfb, cf.nfc, batch),
+                "config": {"workload": ("%s: %s VGG %s w%da%d %d/%d/%d x %d/%d/%d, batch %d per GPU" % (
+                               args.workload, cf.dataset, cf.network_type, cf.wbits, cf.abits, cf.nla, cf.nlb, cf.nlc, cf.nfa, cf.nfb, cf.nfc, batch))
+                           if cf.architecture == "VGG" else ("%s: %s ResNet-%d %s w%da%d, batch %d per GPU" % (
+                               args.workload, cf.dataset, 6 * cf.nres + 2, cf.network_type, cf.wbits, cf.abits, batch)),
                            "global_batch": batch * world, "parallelism": "batch-sharded x%d, NCCL logit all-gather" % world,
                            "l2_policy": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotated every step" % (nbuf, nbuf * batch * img_bytes / 1e6),
                            "cuda_graphs": graphs is not None, "streams": NS, "kernels": args.kernels,

@@ -87,6 +87,7 @@ int qnnb_pack_weights(int32_t mode, int32_t nb, float H, const float* w_hwio, in
 int qnnb_conv2d_tc_supported(const qnnb_conv_desc* d) {
   if (!d || validate_conv(*d) != QNNB_OK) return 0;
   const char* why = "";
+  if (d->in_kind == QNNB_KIND_F32) return conv_f32_tc_supported(*d, &why) ? 1 : 0;
   return conv_tc_supported(*d, &why) ? 1 : 0;
 }
 
@@ -110,6 +111,12 @@ int qnnb_conv2d(const qnnb_conv_desc* d, const void* x, const void* w, void* y, 
   QNNB_CHECK_ARG(x && w && y, "conv2d: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const char* why = "";
+  if (d->in_kind == QNNB_KIND_F32 && (d->impl == QNNB_IMPL_AUTO || d->impl == QNNB_IMPL_TCGEN05)) {
+    // fp32 activations: bf16-split tensor-core kernel where the shape allows it
+    if (conv_f32_tc_supported(*d, &why)) return launch_conv_f32_tc(*d, x, w, y, st);
+    if (d->impl == QNNB_IMPL_TCGEN05) { set_error("conv2d: tcgen05 path does not cover this shape: %s", why); return QNNB_EUNSUPPORTED; }
+    return launch_conv_generic(*d, x, w, y, st);
+  }
   const bool tc_ok = conv_tc_supported(*d, &why);
   if (d->impl == QNNB_IMPL_TCGEN05_V1) {
     if (!tc_ok || !conv_tc_v1_supported(*d)) { set_error("conv2d: tcgen05 v1 kernel does not cover this shape"); return QNNB_EUNSUPPORTED; }

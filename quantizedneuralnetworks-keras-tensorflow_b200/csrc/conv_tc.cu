@@ -26,6 +26,7 @@
 // Pipelines: smem ring full/empty (TMA <-> MMA), 2 TMEM accumulators full/empty (MMA <-> epilogue),
 // persistent static tile schedule.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 
@@ -39,177 +40,7 @@ constexpr int UMMA_K = 32;    // int8
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// latency-critical wait (TMA producer / MMA issuer: one thread each): plain try_wait spin
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 26)) __trap();     // a broken pipeline must fault, not hang the GPU
-  }
-}
-// many-thread wait (epilogue / im2col warps): let the hardware park the warp (suspend-time hint, ns) instead of
-// burning issue slots the MMA-feeding warps could use
-__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 20000;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
-  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// 32 lanes x 64 consecutive columns: thread t of the warp receives lane (base_lane + t), columns c..c+63
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, int (&v)[64]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]),
-        "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]),
-        "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]),
-        "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-      : "r"(taddr)
-      : "memory");
-}
-
-// tcgen05.wait::ld that also "redefines" the 64 destination registers of an earlier tmem_ld64, so the compiler
-// cannot schedule any use of them above the wait (needed once loads are issued ahead of their use)
-__device__ __forceinline__ void tmem_ld_wait_dep(int (&v)[64]) {
-  asm volatile(
-      "tcgen05.wait::ld.sync.aligned;"
-      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
-        "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
-        "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
-        "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]), "+r"(v[32]), "+r"(v[33]), "+r"(v[34]), "+r"(v[35]), "+r"(v[36]),
-        "+r"(v[37]), "+r"(v[38]), "+r"(v[39]), "+r"(v[40]), "+r"(v[41]), "+r"(v[42]), "+r"(v[43]), "+r"(v[44]), "+r"(v[45]),
-        "+r"(v[46]), "+r"(v[47]), "+r"(v[48]), "+r"(v[49]), "+r"(v[50]), "+r"(v[51]), "+r"(v[52]), "+r"(v[53]), "+r"(v[54]),
-        "+r"(v[55]), "+r"(v[56]), "+r"(v[57]), "+r"(v[58]), "+r"(v[59]), "+r"(v[60]), "+r"(v[61]), "+r"(v[62]), "+r"(v[63])
-      :
-      : "memory");
-}
-
-// UMMA shared-memory matrix descriptor, K-major operand whose rows are KC bytes wide and stored with the
-// KC-byte swizzle (KC = 64 or 128): 8-row groups are 8*KC bytes apart (SBO); LBO is unused for swizzled
-// K-major layouts (set to 16 B); version = 1 (Blackwell); layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
-template <int KC>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  constexpr uint64_t layout = (KC == 128) ? 2ull : 4ull;
-  constexpr uint64_t sbo = (8 * KC) >> 4;
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= sbo << 32;
-  d |= (uint64_t)1 << 46;
-  d |= layout << 61;
-  return d;
-}
-
-// Un-swizzled K-major "interleaved" layout: 8 rows x 16 B core matrices; consecutive 16-byte K chunks of a
-// row group are lbo bytes apart, 8-row groups sbo bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc_interleaved(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;                                      // layout_type 0 = SWIZZLE_NONE
-}
-
-// instruction descriptor: dense, S32 accumulate, int8 operands (signedness per operand), both K-major
-__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed, bool b_signed) {
-  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
+using namespace tcx;
 
 // Optional device-side timeline (debug/profiling only): when a buffer is registered with qnnb_debug_set_trace(),
 // CTA 0 records globaltimer stamps of its pipeline events as (tag, value) pairs.  NULL in production.
@@ -239,10 +70,14 @@ __device__ __forceinline__ void trace(const Trace& tr, int tag, int idx) {
 #endif
 }
 
+// tile -> (channel tile, column tile, row tile, image group)
+struct TileCoord { int mt, tw_i, th_i, pt; };
+
 struct TcParams {
   Trace tr;
   int n, h, w, cin, cout;
   int tiles_w, tiles_h, tiles_n, m_tiles, num_tiles;
+  FastDiv fd_m, fd_w, fd_h;
   int kchunks;            // cin / KC
   int out_pitch;          // bytes per staged output row = channels per TMA-store box (<= 128)
   void* y;
@@ -255,6 +90,17 @@ constexpr bool SPLIT_EPILOGUE = false;
 #else
 constexpr bool SPLIT_EPILOGUE = true;
 #endif
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+  TileCoord t;
+  int q = fdiv(tile, p.fd_m);
+  t.mt = tile - q * p.m_tiles;
+  int q2 = fdiv(q, p.fd_w);
+  t.tw_i = q - q2 * p.tiles_w;
+  t.pt = fdiv(q2, p.fd_h);
+  t.th_i = q2 - t.pt * p.tiles_h;
+  return t;
+}
+
 constexpr int EPI_BAR_ID = 2;                      // named barriers 2 and 3
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 
@@ -320,11 +166,9 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
   QConst qc = {1.f, 0.f, 1.f, 0.f};
   int it = SPLIT ? egrp : 0;
   for (int tile = blockIdx.x + it * (int)gridDim.x; tile < p.num_tiles; tile += IT_STEP * (int)gridDim.x, it += IT_STEP) {
-    const int mt = tile % p.m_tiles;
-    int pt = tile / p.m_tiles;
-    const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
-    const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
-    const int n0 = pt * TN, h0 = th_i * (TH * GROUPS), w0 = tw_i * TW;
+    const TileCoord tc = decode_tile(p, tile);
+    const int mt = tc.mt;
+    const int n0 = tc.pt * TN, h0 = tc.th_i * (TH * GROUPS), w0 = tc.tw_i * TW;
     const int ch = mt * TILE_M + ch_in_tile;
     const bool ch_ok = ch < p.cout;
     const bool warp_active = (mt * TILE_M + ch_in_tile - lane) < p.cout; // warp-uniform
@@ -469,6 +313,7 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
           __syncwarp();
           tmem_ld64(taddr + 64 * j, v);
           tmem_ld_wait_dep(v);
+          if (leader) trace(p.tr, 20 + j, tile);
           if (j == 3) {
             tc_fence_before();
             __syncwarp();
@@ -601,11 +446,9 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles;
-        int pt = tile / p.m_tiles;
-        const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
-        const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
-        const int n0 = pt * TN, h0 = th_i * TH, w0 = tw_i * TW;
+        const TileCoord tc = decode_tile(p, tile);
+        const int mt = tc.mt;
+        const int n0 = tc.pt * TN, h0 = tc.th_i * TH, w0 = tc.tw_i * TW;
         for (int ks = 0; ks < ksteps; ++ks) {
           const int tap = ks / p.kchunks, kc = ks % p.kchunks;
           const int r = tap / 3, s = tap % 3;
@@ -751,11 +594,9 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   const uint32_t tmem_base = *tmem_slot_gen;
 
   auto decode = [&](int tile, int& mt, int& n0, int& h0, int& w0) {
-    mt = tile % p.m_tiles;
-    int pt = tile / p.m_tiles;
-    const int tw_i = pt % p.tiles_w; pt /= p.tiles_w;
-    const int th_i = pt % p.tiles_h; pt /= p.tiles_h;
-    n0 = pt * TN; h0 = th_i * TH; w0 = tw_i * 8;
+    const TileCoord tc = decode_tile(p, tile);
+    mt = tc.mt;
+    n0 = tc.pt * TN; h0 = tc.th_i * TH; w0 = tc.tw_i * 8;
   };
 
   if (warp == 0) {
@@ -778,7 +619,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     if (lane == 0) {
       int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles;
+        const int mt = tile - fdiv(tile, p.fd_m) * p.m_tiles;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(aempty(as), aphase ^ 1u);
@@ -995,7 +836,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int mt = tile % p.m_tiles;
+        const int mt = tile - fdiv(tile, p.fd_m) * p.m_tiles;
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -1025,9 +866,9 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
     constexpr int PER = (ITEMS + K5_PRODUCERS - 1) / K5_PRODUCERS;
     uint32_t g0[PER], g1[PER], g2[PER];
     auto issue_loads = [&](int tile) {
-      int pt = tile / p.m_tiles;
-      const int th_i = pt % p.tiles_h;
-      const int nimg = pt / p.tiles_h;
+      const int pt = fdiv(tile, p.fd_m);
+      const int nimg = fdiv(pt, p.fd_h);
+      const int th_i = pt - nimg * p.tiles_h;
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
         const int item = t + u * K5_PRODUCERS;
@@ -1096,31 +937,6 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)sym;
-  }
-  return fn;
-}
-
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
-}
-
 struct Geometry { int tw, th, tn; };
 
 bool pick_geometry(int h, int w, Geometry* g) {
@@ -1199,6 +1015,7 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
   p.tiles_n = d.n;
   p.m_tiles = (G == 2) ? 1 : ceil_div(d.cout, TILE_M);
   p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
+  p.fd_m = make_fastdiv(p.m_tiles); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h);
   p.kchunks = 1;
   p.out_pitch = d.cout < TILE_M ? d.cout : TILE_M;
   p.y = y;
@@ -1332,6 +1149,7 @@ int launch_conv_tc_v2(const qnnb_conv_desc& d, const void* x, const void* w, voi
   p.tiles_n = ceil_div(d.n, g.tn);
   p.m_tiles = d.cout / TILE_M;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.m_tiles;
+  p.fd_m = make_fastdiv(p.m_tiles); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h);
   p.kchunks = d.cin / KC;
   p.out_pitch = TILE_M;
   p.y = y;
@@ -1352,6 +1170,8 @@ bool conv_tc_v1_supported(const qnnb_conv_desc& d) {
 
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   Geometry g;
+  // tile indices must stay below 2^24 (FastDiv): at most 8 tiles per image on any supported shape
+  if ((long long)d.n * ((d.h + 7) / 8) * ((d.w + 7) / 8) * ((d.cout + 127) / 128) >= (1ll << 24)) { *why = "batch too large for one launch"; return false; }
   if (first_layer_shape(d)) return epilogue_ok(d, why);
   if (d.in_kind != QNNB_KIND_I8) { *why = "input must be int8 levels (or uint8 32-wide RGB for the first layer)"; return false; }
   if (d.kh != 3 || d.kw != 3 || d.stride != 1) { *why = "only 3x3 stride 1"; return false; }
@@ -1413,6 +1233,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   p.tiles_n = ceil_div(d.n, g.tn);
   p.m_tiles = d.cout / TILE_M;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.m_tiles;
+  p.fd_m = make_fastdiv(p.m_tiles); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h);
   p.kchunks = d.cin / KC;
   p.out_pitch = TILE_M;
   p.y = y;

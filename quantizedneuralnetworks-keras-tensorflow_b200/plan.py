@@ -267,19 +267,23 @@ class Plan:
             env["logits"] = logits
         self.launches += 1
 
+    def run_step(self, st, env):
+        """Launch one fused step on the tensors in ``env`` (tensor index -> QTensor)."""
+        if st.kind == "conv":
+            self._run_conv(st, env)
+        elif st.kind == "dense":
+            self._run_dense(st, env)
+        else:
+            ins = [env[s] for s in st.src]
+            y = st.layer.call(ins if isinstance(st.layer, E.Add) else ins[0])
+            env[st.out] = y if isinstance(y, K.QTensor) else K.as_qtensor(y)
+            self.launches += 1
+
     def run(self, x) -> dict:
         """One forward over a device batch.  Returns the environment (tensor index -> QTensor)."""
         env = {self.input_idx: K.as_qtensor(x)}
         for st in self.steps:
-            if st.kind == "conv":
-                self._run_conv(st, env)
-            elif st.kind == "dense":
-                self._run_dense(st, env)
-            else:
-                ins = [env[s] for s in st.src]
-                y = st.layer.call(ins if isinstance(st.layer, E.Add) else ins[0])
-                env[st.out] = y if isinstance(y, K.QTensor) else K.as_qtensor(y)
-                self.launches += 1
+            self.run_step(st, env)
         return env
 
     def forward(self, x, return_logits=False):

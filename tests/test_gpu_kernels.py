@@ -473,3 +473,55 @@ def test_conv2d_sign_to_int8_levels_bit_exact(case):
     assert set(np.unique(got)) <= {-1, 1}
     bad = np.argwhere(got != want.astype(np.int32))
     assert bad.shape[0] == 0, "sign mismatches: %d of %d, first %s" % (bad.shape[0], want.size, bad[:8].tolist())
+
+
+# --------------------------------------------------------------------------- K4: fp32 activations on the tensor cores (bf16 x 3 split)
+F32_TC_CASES = [
+    # n, h, w, cin, cout, wkind, nb, act, residual, bias
+    (2, 32, 32, 16, 16, "quantized", 4, "leaky", True, False),     # ResNet stack 0 block end
+    (3, 16, 16, 32, 32, "quantized", 4, "leaky", False, True),     # ResNet stack 1 first conv of a block
+    (5, 8, 8, 64, 64, "ternary", 2, "leaky", True, False),         # stack 2, two images per tile, ragged pair
+    (2, 16, 24, 16, 48, "binary", 1, None, False, True),           # Cout != Cin, no activation
+    (1, 32, 8, 48, 16, "quantized", 8, "leaky", False, False),     # three channel chunks
+    (40, 32, 32, 16, 16, "quantized", 4, "leaky", True, True),     # 320 tiles: persistent loop, ring wrap-around
+]
+
+
+@pytest.mark.parametrize("case", F32_TC_CASES, ids=["n%d_%dx%d_%d-%d_%s%d_%s%s" % (c[0], c[1], c[2], c[3], c[4], c[5][:3], c[6], c[7], "_res" if c[8] else "") for c in F32_TC_CASES])
+def test_conv2d_f32_tcgen05_tolerance(case):
+    """fp32 activations x exact integer kernels on tcgen05 kind::f16 with the activations split into three bf16
+    terms: products are exact, accumulation is fp32 in TMEM -> same tolerance class as the FFMA kernel."""
+    q, L, K = _mods()
+    n, h, w, cin, cout, wkind, nb, act, use_res, use_bias = case
+    rng = np.random.default_rng(_seed(("f32tc",) + case))
+    x = rng.normal(0, 1, size=(n, h, w, cin)).astype(F32)
+    x[0, 0, 0, :] = 0.0
+    x[0, -1, -1, :] = F32(1e-6)           # tiny values: the low split terms matter
+    x[0, 1, 1, :] = F32(123.456)
+    kernel = rng.uniform(-1, 1, size=(3, 3, cin, cout)).astype(F32)
+    fan = 9 * cin
+    bias = rng.uniform(-0.3, 0.3, size=cout).astype(F32) if use_bias else None
+    bn = (rng.uniform(0.3, 0.9, cout).astype(F32) * rng.choice([1, 1, -1], cout).astype(F32), rng.uniform(-0.2, 0.2, cout).astype(F32),
+          rng.uniform(-0.2, 0.2, cout).astype(F32), (rng.uniform(0.5, 1.5, cout) * fan * 0.3).astype(F32))
+    residual = rng.normal(0, 0.5, size=(n, h, w, cout)).astype(F32) if use_res else None
+    want, _ = oracle_layer(x, "f32", 1.0, kernel, wkind, nb, 1.0, 1, bias=bias, bn=bn, eps=1e-3, residual=residual, res_mul=0.5,
+                           act=act, abits=4)
+    mode = {"quantized": L.W_QUANT, "binary": L.W_BINARY, "ternary": L.W_TERNARY}[wkind]
+    wp = K.pack_weights(dev(kernel), mode, nb, 1.0, L.WFMT_I8)
+    wscale = 1.0 / (1 << (nb - 1)) if wkind == "quantized" else 1.0
+    i_, s_ = K.bn_constants(*bn, 1e-3)
+    res_q = K.QTensor("f32", dev(residual), 1.0, cout) if use_res else None
+    actc = {"leaky": L.ACT_LEAKY, None: L.ACT_NONE}[act]
+    epi = K.make_epilogue(F32(wscale), bias=dev(bias) if use_bias else None, bn_inv=dev(i_), bn_shift=dev(s_), residual=res_q,
+                          res_mul=0.5, act=actc, leaky_alpha=0.3)
+    xq = K.QTensor("f32", dev(x), 1.0, cin)
+    assert K.conv2d_on_tensor_cores(xq, 3, 3, cout, 1, epi, L.IMPL_TCGEN05)
+    y = K.conv2d(xq, wp, 3, 3, cout, 1, epi, impl=L.IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    got = y.data.cpu().numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    assert err.max() <= 1e-5 * np.abs(want).max(), "max abs err %g (rel %g) at %s" % (err.max(), err.max() / np.abs(want).max(), np.unravel_index(err.argmax(), err.shape))
+    # and it agrees with the CUDA-core kernel to the same tolerance
+    y2 = K.conv2d(xq, wp, 3, 3, cout, 1, epi, impl=L.IMPL_GENERIC).data.cpu().numpy()
+    assert np.abs(got - y2).max() <= 1e-5 * np.abs(want).max()

@@ -39,7 +39,7 @@ for wp_ in range(15):
         ev.append((int(reg[3 + 2 * i]), int(reg[2 + 2 * i]) >> 32, int(reg[2 + 2 * i]) & 0xffffffff, wp_))
 ev.sort()
 t0 = ev[0][0]
-names = {11: "epi loop top", 12: "epi chunk0 loaded", 13: "epi chunk1 loaded", 14: "epi math done", 10: "producer halo staged", 1: "entry", 2: "setup done", 3: "producer tile ready", 4: "mma acc free", 5: "mma first operands", 6: "mma tile issued", 7: "epi acc ready", 8: "epi stored", 9: "teardown"}
+names = {20: "epi chunk0 loaded", 21: "epi chunk1 loaded", 22: "epi chunk2 loaded", 23: "epi chunk3 loaded", 11: "epi loop top", 12: "epi chunk0 loaded", 13: "epi chunk1 loaded", 14: "epi math done", 10: "producer halo staged", 1: "entry", 2: "setup done", 3: "producer tile ready", 4: "mma acc free", 5: "mma first operands", 6: "mma tile issued", 7: "epi acc ready", 8: "epi stored", 9: "teardown"}
 print("kernel event time %.1f us, %d trace events" % (e0.elapsed_time(e1) * 1e3, len(ev)))
-for t, tag, idx, wp_ in ev:
+for t, tag, idx, wp_ in ev[:int(os.environ.get("TRACE_MAX", "400"))]:
     print("%8d ns  w%-2d %-20s tile %d" % (t - t0, wp_, names.get(tag, tag), idx))
