@@ -182,6 +182,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
 bool conv_f32_tc_supported(const qnnb_conv_desc& d, const char** why);
 int launch_conv_f32_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
 void set_trace_buffer(unsigned long long* buf, int cap);
+unsigned long long* get_trace_buffer();
 int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st);
 
 }  // namespace qnnb

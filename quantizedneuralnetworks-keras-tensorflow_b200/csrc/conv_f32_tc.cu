@@ -23,14 +23,23 @@
 //               (un-swizzled K-major core matrices: 8 consecutive pixels = 8 rows x 16 B)
 //   warp 1      27 MMAs (3 planes x 9 taps, kind::f16, M=128, N=cout, K=16): tap (r,s) is the SAME plane viewed
 //               through a descriptor shifted by (r*TN*10 + s) pixels, group stride = one halo row (as in K1 v2);
-//               all taps' kernels stay resident in shared memory as bf16
+//               all taps' kernels stay resident in shared memory as bf16.  With N this small an MMA occupies the
+//               tensor pipe for a few cycles but its accumulate latency is ~100, so a chain of MMAs into ONE
+//               accumulator runs at latency (measured: ~110 cycles per MMA for N = 16, 32 and 64 alike).  The MMAs
+//               of a tile therefore rotate over NP independent partial accumulators (NP x cout TMEM columns), which
+//               the epilogue adds up.
 //   warps 4-7   epilogue: tcgen05.ld 16 columns at a time, scale / bias / BN / residual / LeakyReLU in the fixed
-//               fp32 op order of common.cuh, 128-bit stores
+//               fp32 op order of common.cuh.  The residual tile of the shortcut branch is TMA-loaded into a ring of
+//               [pixel][channel] tiles (64B/128B swizzle: a thread reads its own pixel row without bank conflicts);
+//               the result overwrites it in place and leaves through one TMA store per tile, so the epilogue
+//               never waits on a global-memory round trip and HBM sees full 128-byte rows.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
+#include <stdlib.h>
 
 namespace qnnb {
 
@@ -38,20 +47,33 @@ namespace {
 
 using namespace tcx;
 
-constexpr int F_THREADS = 512;
+// warp roles: 0 = halo TMA, 1 and 3 = MMA issuers (even / odd tiles), 2 = TMEM allocator + shortcut-tile TMA,
+// 4..11 = two epilogue groups of four warps (even / odd tiles), 12..17 = converters
 constexpr int F_CVT_WARPS = 8;
 constexpr int F_CVT_THREADS = F_CVT_WARPS * 32;
-constexpr int F_EPI_WARPS = 4;
+constexpr int F_EPI_WARPS = 4;       // per group
+constexpr int F_EPI_GROUPS = 2;
+constexpr int F_CVT_WARP0 = 4 + F_EPI_GROUPS * F_EPI_WARPS;
+constexpr int F_THREADS = (F_CVT_WARP0 + F_CVT_WARPS) * 32;
 constexpr int F_KC = 16;             // channels per pipeline unit (= one bf16 MMA K step)
-constexpr int F_FSTAGES = 4;         // fp32 halo ring
+constexpr int F_FSTAGES = 8;         // fp32 halo ring (at most; the host picks the depth that fits)
+constexpr int F_RSTAGES = 6;         // residual / output tile ring (at most)
 constexpr int F_PSTAGES = 3;         // bf16 plane ring
-constexpr int F_ACCS = 4;            // TMEM accumulators, 64 columns each
+constexpr int F_EPI_BAR = 2;         // named barriers 2, 3: one per epilogue group
+constexpr int F_ACCS = 4;            // TMEM accumulator slots in flight (at most)
 constexpr int F_MAXC = 64;           // channel limit (Cin and Cout)
 constexpr int F_W_BYTES = 9 * F_MAXC * F_MAXC * 2;
 
 struct F32Params {
   int n, h, w, cin, cout;
   int tiles_w, tiles_h, num_tiles, kchunks;
+  int f_stages, r_stages;            // ring depths chosen by the host
+  int in_merged;                     // Cin == 16: the halo box is a 3-D box over (W*C, N, H) -- rows of 640 B instead of 64 B
+  unsigned long long* dbg;           // QNNB_TRACE builds: CTA 0 timeline (region = role * 1024 words: [count, (tag<<32|idx, ns)...])
+  int exp_mode;                      // diagnostics only (QNNB_K4_EXP): 1 = issue one plane's MMAs, 2 = converters skip the split, 3 = epilogue skips math
+  int np, accs, acc_cols;            // partial accumulators per tile, tiles in flight in TMEM, columns per tile (np * cout)
+  int off_p, off_w, off_r, off_c, off_bar;   // shared-memory offsets (bytes)
+  int r_bytes;                       // one residual / output tile: 128 px x cout floats
   FastDiv fd_w, fd_h;
   const int8_t* wpk;                 // packed kernel levels [cout][3][3][cin]
   float* y;
@@ -67,22 +89,37 @@ struct F32Smem {
   static constexpr int K8_BYTES = HALO_PX * 16 + ((HALO_PX * 16) % 128 == 64 ? 0 : 64);
   static constexpr int PLANE_BYTES = 2 * K8_BYTES;
   static constexpr int PSTAGE_BYTES = 3 * PLANE_BYTES;
-  static constexpr int F_OFF = 0;
-  static constexpr int P_OFF = (F_OFF + F_FSTAGES * F_BYTES + 127) / 128 * 128;
-  static constexpr int W_OFF = (P_OFF + F_PSTAGES * PSTAGE_BYTES + 127) / 128 * 128;
-  static constexpr int C_OFF = W_OFF + F_W_BYTES;            // bias[64], inv[64], shift[64]
-  static constexpr int BAR_OFF = C_OFF + 3 * F_MAXC * 4;
-  static constexpr int TOTAL = BAR_OFF + 256 + 128;
   static_assert(F_BYTES % 128 == 0, "TMA destination alignment");
 };
 
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void ftrace(const F32Params& p, int role, int tag, int idx) {
+#ifdef QNNB_TRACE
+  if (p.dbg != nullptr && blockIdx.x == 0) {
+    unsigned long long* reg = p.dbg + role * 1024;
+    const unsigned long long k = reg[0];
+    if (k < 500) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      reg[2 + 2 * k] = ((unsigned long long)tag << 32) | (unsigned)idx;
+      reg[3 + 2 * k] = t;
+      reg[0] = k + 1;
+    }
+  }
+#endif
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32.  The descriptors are passed as (low, high) words: the issuing
+// thread is a single thread whose instruction count per MMA is what bounds this kernel (N is tiny), so the loop keeps
+// the high words constant and only adds small offsets to the low words (start address field, 16-byte units).
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -116,23 +153,28 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& hi, uint32_
 
 template <int TH>
 __global__ void __launch_bounds__(F_THREADS, 1)
-conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const F32Params p) {
+conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_r,
+                      const __grid_constant__ CUtensorMap map_y, const F32Params p) {
   using SL = F32Smem<TH>;
   constexpr int TN = SL::TN;
   constexpr int HALO_PX = SL::HALO_PX;
 
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzled residual tiles need 1024 B
   uint8_t* sg = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + SL::BAR_OFF;
+  const uint32_t bar_base = smem_base + p.off_bar;
   auto ffull = [&](int s) { return bar_base + 8u * s; };
   auto fempty = [&](int s) { return bar_base + 8u * (F_FSTAGES + s); };
   auto pfull = [&](int b) { return bar_base + 8u * (2 * F_FSTAGES + b); };
   auto pempty = [&](int b) { return bar_base + 8u * (2 * F_FSTAGES + F_PSTAGES + b); };
   auto tfull = [&](int a) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + a); };
   auto tempty = [&](int a) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + F_ACCS + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + SL::BAR_OFF + 8 * (2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS));
+  auto rfull = [&](int r) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS + r); };
+  auto rempty = [&](int r) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS + F_RSTAGES + r); };
+  constexpr int NBARS = 2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS + 2 * F_RSTAGES;
+  const uint32_t tmem_slot = bar_base + 8u * NBARS;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + p.off_bar + 8 * NBARS);
+  const bool has_res = p.epi.res_kind == QNNB_KIND_F32;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,9 +201,9 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const F32Params
         const __nv_bfloat162 v = __floats2bfloat162_rn((float)b0, (float)b1);
         o[j] = *reinterpret_cast<const uint32_t*>(&v);
       }
-      *reinterpret_cast<uint4*>(sg + SL::W_OFF + (size_t)i * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(sg + p.off_w + (size_t)i * 16) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    float* cst = reinterpret_cast<float*>(sg + SL::C_OFF);
+    float* cst = reinterpret_cast<float*>(sg + p.off_c);
     for (int c = threadIdx.x; c < F_MAXC; c += F_THREADS) {
       const bool ok = c < cout;
       cst[c] = (p.epi.bias != nullptr && ok) ? __ldg(p.epi.bias + c) : 0.f;
@@ -169,15 +211,16 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const F32Params
       cst[2 * F_MAXC + c] = (p.epi.bn_inv != nullptr && ok) ? __ldg(p.epi.bn_shift + c) : 0.f;
     }
   }
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_x);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_y); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < F_FSTAGES; ++s) { mbar_init(ffull(s), 1); mbar_init(fempty(s), F_CVT_WARPS); }
+    for (int r = 0; r < F_RSTAGES; ++r) { mbar_init(rfull(r), 1); mbar_init(rempty(r), 1); }
     for (int b = 0; b < F_PSTAGES; ++b) { mbar_init(pfull(b), F_CVT_WARPS); mbar_init(pempty(b), 1); }
     for (int a = 0; a < F_ACCS; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), F_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   fence_proxy_async();                   // resident kernel written through the generic proxy, read by the tensor core
@@ -196,89 +239,161 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const F32Params
 
   if (warp == 0) {
     // ===================== TMA: fp32 halo tile per (tile, chunk) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int n0, h0, w0;
         decode(tile, n0, h0, w0);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(fempty(s), ph ^ 1u);
+          ftrace(p, 0, 1, tile);                      // TMA: halo slot free, load issued
           mbar_expect_tx(ffull(s), SL::F_BYTES);
-          tma_load_4d(smem_base + SL::F_OFF + s * SL::F_BYTES, &map_x, ffull(s), kc * F_KC, w0 - 1, n0, h0 - 1);
-          if (++s == F_FSTAGES) { s = 0; ph ^= 1u; }
+          if (p.in_merged) tma_load_3d(smem_base + 0 + s * SL::F_BYTES, &map_x, ffull(s), (w0 - 1) * F_KC, n0, h0 - 1);
+          else tma_load_4d(smem_base + 0 + s * SL::F_BYTES, &map_x, ffull(s), kc * F_KC, w0 - 1, n0, h0 - 1);
+          if (++s == p.f_stages) { s = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 2) {
+    // ===================== TMA: shortcut (residual) / output tile ring =====================
+    // its own thread: a single-threaded loop pays a few hundred ns per barrier wait, and this wait depends on the
+    // epilogue (buffer release), which must not hold back the halo loads of the tiles behind it
+    if (elect_one()) {
+      int r = 0; uint32_t rph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int n0, h0, w0;
+        decode(tile, n0, h0, w0);
+        // acquire the buffer, then either fill it or just hand it over
+        mbar_wait(rempty(r), rph ^ 1u);
+        ftrace(p, 0, 2, tile);                        // TMA: residual slot free
+        if (has_res) {
+          mbar_expect_tx(rfull(r), p.r_bytes);
+          if (cout == 16) tma_load_4d(smem_base + p.off_r + r * p.r_bytes, &map_r, rfull(r), 0, w0 >> 1, n0, h0);
+          else
+            for (int sub = 0; sub * 32 < cout; ++sub)
+              tma_load_4d(smem_base + p.off_r + r * p.r_bytes + sub * (128 * 128), &map_r, rfull(r), sub * 32, w0, n0, h0);
+        } else {
+          mbar_arrive(rfull(r));
+        }
+        if (++r == p.r_stages) { r = 0; rph ^= 1u; }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers =====================
+    // The issue loop is single-threaded and, with MMAs this small, it IS the critical path (timeline trace: ~70 cycles
+    // per MMA plus ~0.4 us of barrier waits per tile).  Two warps therefore issue alternate tiles: warp 1 the even
+    // iterations, warp 3 the odd ones; each walks the whole unit sequence to keep its ring indices in step.
+    const int my_par = warp == 1 ? 0 : 1;
+    if (elect_one()) {
       // instruction descriptor: dense, F32 accumulate, BF16 x BF16, both K-major, N = cout, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t w_lbo = (uint32_t)cout * 16u;
+      // un-swizzled K-major descriptors: low word = start address >> 4 | (K-chunk stride >> 4) << 16,
+      //                                  high word = 8-row group stride >> 4 | version 1 (bit 46)
+      // A: 16 groups of 8 pixels, one halo row (10 px x 16 B) apart; the two 16-byte K chunks K8_BYTES apart
+      // B: 8-channel groups 128 B apart; the two K chunks cout * 16 B apart
+      const uint32_t a_hi = (160u >> 4) | (1u << 14);
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo0 = (((smem_base + p.off_p) & 0x3FFFFu) >> 4) | ((uint32_t)(SL::K8_BYTES >> 4) << 16);
+      const uint32_t b_lo0 = (((smem_base + p.off_w) & 0x3FFFFu) >> 4) | ((uint32_t)cout << 16);
+      const uint32_t w_tap = (uint32_t)(kchunks * 2 * cout);      // 16-byte units between consecutive taps of the kernel
+      const bool np3 = p.np == 3;
       int b = 0; uint32_t pph = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it % F_ACCS;
-        const uint32_t acc_phase = (uint32_t)(it / F_ACCS) & 1u;
+        if ((it & 1) != my_par) {
+          // the other issuer's tile: still observe every unit's barrier phase -- a parity wait can only tell adjacent
+          // phases apart, so a waiter that skipped a whole ring revolution would alias onto an older phase
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(pfull(b), pph);
+            if (++b == F_PSTAGES) { b = 0; pph ^= 1u; }
+          }
+          continue;
+        }
+        const int acc = it % p.accs;
+        const uint32_t acc_phase = (uint32_t)(it / p.accs) & 1u;
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(pfull(b), pph);
+          ftrace(p, 2, 6, tile);                      // MMA: planes ready
           tc_fence_after();
-          const uint32_t planes = smem_base + SL::P_OFF + b * SL::PSTAGE_BYTES;
-#pragma unroll 1
+          const uint32_t a_unit = a_lo0 + (uint32_t)(b * (SL::PSTAGE_BYTES >> 4));
+          const uint32_t b_unit = b_lo0 + (uint32_t)(kc * 2 * cout);
+          const uint32_t later = kc > 0 ? 1u : 0u;
+#pragma unroll
           for (int split = 0; split < 3; ++split) {
-            const uint32_t plane = planes + split * SL::PLANE_BYTES;
+            if (p.exp_mode == 1 && split > 0) break;
+            // np == 3: one partial accumulator per bf16 plane (three independent MMA chains)
+            const uint32_t d = d_tmem + (np3 ? (uint32_t)(split * cout) : 0u);
+            const uint32_t first = (split == 0 || np3) ? later : 1u;
+            uint32_t b_lo = b_unit;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const int r = tap / 3, s = tap - 3 * r;
-              // A: 16 groups of 8 pixels, one halo row (10 px x 16 B) apart; the two 16-byte K chunks K8_BYTES apart
-              const uint64_t a_desc = make_smem_desc_interleaved(plane + (uint32_t)((r * TN * 10 + s) * 16), SL::K8_BYTES, 160);
-              const uint64_t b_desc = make_smem_desc_interleaved(smem_base + SL::W_OFF + (uint32_t)((tap * kchunks + kc) * 2) * w_lbo, w_lbo, 128);
-              umma_bf16(d_tmem, a_desc, b_desc, idesc, (kc > 0 || split > 0 || tap > 0) ? 1u : 0u);
+              const int r = tap / 3, sft = tap - 3 * r;
+              umma_bf16(d, a_unit + (uint32_t)(split * (SL::PLANE_BYTES >> 4) + r * TN * 10 + sft), a_hi, b_lo, b_hi, idesc,
+                        tap == 0 ? first : 1u);
+              b_lo += w_tap;
             }
           }
           umma_commit(pempty(b));
           if (++b == F_PSTAGES) { b = 0; pph ^= 1u; }
         }
         umma_commit(tfull(acc));
+        ftrace(p, 2, 7, tile);                        // MMA: tile issued
       }
     }
-  } else if (warp >= 4 && warp < 4 + F_EPI_WARPS) {
+  } else if (warp >= 4 && warp < F_CVT_WARP0) {
     // ===================== epilogue: thread = pixel =====================
     const int quarter = warp & 3;
-    const int L = quarter * 32 + lane;               // TMEM lane = pixel of the tile
-    const int g = L >> 3, px = L & 7;
-    const int row = g / TN, img = g % TN;
+    const int L = quarter * 32 + lane;               // TMEM lane = pixel of the tile = row of the residual tile
     const Epi& e = p.epi;
-    const float* cst = reinterpret_cast<const float*>(sg + SL::C_OFF);
+    const float* cst = reinterpret_cast<const float*>(sg + p.off_c);
     const bool has_bias = e.bias != nullptr, has_bn = e.bn_inv != nullptr;
-    const bool has_res = e.res_kind == QNNB_KIND_F32;
     const bool leaky = e.act == QNNB_ACT_LEAKY;
+    const int egrp = (warp - 4) >> 2;                // epilogue group: tiles with (it & 1) == egrp
+    const bool leader = (quarter == 0 && lane == 0);
+    // residual / output tile: 128-byte rows, SWIZZLE_128B.  Cout >= 32: row = pixel, 32 channels per sub-tile;
+    // Cout = 16: row = two neighbouring pixels (the tensor map views the image as [W/2][32 floats])
+    const bool two_px = cout == 16;
+    const int trow = two_px ? (L >> 1) : L;
+    const uint32_t xr = (uint32_t)(trow & 7);        // 16-byte chunk XOR of this row
     int it = 0;
+    int r = 0; uint32_t rph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != egrp) {                        // the other group's tile (r_stages is even: its buffers are never ours)
+        if (++r == p.r_stages) { r = 0; rph ^= 1u; }
+        continue;
+      }
       int n0, h0, w0;
       decode(tile, n0, h0, w0);
-      const int acc = it % F_ACCS;
-      const uint32_t acc_phase = (uint32_t)(it / F_ACCS) & 1u;
-      const int nimg = n0 + img;
-      const bool valid = nimg < p.n;
-      const long long pix = ((long long)nimg * p.h + (h0 + row)) * p.w + (w0 + px);
-      float* yrow = p.y + pix * cout;
-      const float* rrow = reinterpret_cast<const float*>(e.residual) + pix * cout;
+      const int acc = it % p.accs;
+      const uint32_t acc_phase = (uint32_t)(it / p.accs) & 1u;
+      uint8_t* rbuf = sg + p.off_r + r * p.r_bytes;
+      mbar_wait_parked(rfull(r), rph);               // shortcut tile landed (or: buffer is ours)
+      if (leader) ftrace(p, 3, 8, tile);
       mbar_wait_parked(tfull(acc), acc_phase);
+      if (leader) ftrace(p, 3, 9, tile);             // epilogue: accumulator complete
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
       for (int c0 = 0; c0 < cout; c0 += 16) {
+        if (p.exp_mode == 3) { if (c0 == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty(acc)); } continue; }
+        uint8_t* rowp = rbuf + (c0 >> 5) * (128 * 128) + trow * 128;
+        const uint32_t ch0 = two_px ? (uint32_t)((L & 1) * 4) : (uint32_t)((c0 & 31) >> 2);   // first 16-byte chunk of this block
         float4 rs[4];
-        if (has_res && valid) {
+        if (has_res) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rs[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
+          for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4*>(rowp + (((ch0 + j) ^ xr) << 4));
         }
         float v[16];
         __syncwarp();
         tmem_ld16(taddr + (uint32_t)c0, v);
+        for (int part = 1; part < p.np; ++part) {      // add the other partial accumulators
+          float u[16];
+          tmem_ld16(taddr + (uint32_t)(part * cout + c0), u);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(v[j], u[j]);
+        }
         if (c0 + 16 >= cout) {
           // last TMEM read of this tile: hand the accumulator back before the arithmetic
           tc_fence_before();
@@ -297,42 +412,73 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const F32Params
           if (leaky) z = act_leaky(z, e.leaky_alpha);
           v[j] = z;
         }
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(yrow + c0)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(rowp + (((ch0 + j) ^ xr) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
+      fence_proxy_async();                           // result tile -> visible to the TMA store
+      named_bar_sync(F_EPI_BAR + egrp, F_EPI_WARPS * 32);
+      if (leader) {
+        if (two_px) tma_store_4d(&map_y, smem_u32(rbuf), 0, w0 >> 1, n0, h0);
+        else
+          for (int sub = 0; sub * 32 < cout; ++sub)
+            tma_store_4d(&map_y, smem_u32(rbuf + sub * (128 * 128)), sub * 32, w0, n0, h0);
+        tma_store_commit();
+        ftrace(p, 3, 10, tile);                       // epilogue: tile stored
+        // release the buffer as soon as the store has read it (this group has a whole tile of slack before it is needed)
+        tma_store_wait_read();
+        mbar_arrive(rempty(r));
+      }
+      if (++r == p.r_stages) { r = 0; rph ^= 1u; }
     }
-  } else if (warp >= 8) {
+    if (leader) tma_store_wait_all();
+  } else if (warp >= F_CVT_WARP0) {
     // ===================== converters: fp32 halo -> three bf16 planes =====================
-    const int t = threadIdx.x - 8 * 32;
+    const int t = threadIdx.x - F_CVT_WARP0 * 32;
     int s = 0; uint32_t fph = 0;
     int b = 0; uint32_t pph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait_parked(ffull(s), fph);
+        if (t == 0) ftrace(p, 1, 3, tile);            // converter: halo landed
         mbar_wait_parked(pempty(b), pph ^ 1u);
-        const uint8_t* fsrc = sg + SL::F_OFF + s * SL::F_BYTES;
-        uint8_t* pdst = sg + SL::P_OFF + b * SL::PSTAGE_BYTES;
-        for (int item = t; item < HALO_PX * 2; item += F_CVT_THREADS) {
-          const int hp = item >> 1, half = item & 1;
-          const float4 a = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32);
-          const float4 c = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32 + 16);
-          uint32_t hi[4], mid[4], lo[4];
-          split3(a.x, a.y, hi[0], mid[0], lo[0]);
-          split3(a.z, a.w, hi[1], mid[1], lo[1]);
-          split3(c.x, c.y, hi[2], mid[2], lo[2]);
-          split3(c.z, c.w, hi[3], mid[3], lo[3]);
-          uint8_t* d = pdst + half * SL::K8_BYTES + hp * 16;
-          *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(d + SL::PLANE_BYTES) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-          *reinterpret_cast<uint4*>(d + 2 * SL::PLANE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (t == 0) ftrace(p, 1, 4, tile);            // converter: plane slot free
+        const uint8_t* fsrc = sg + 0 + s * SL::F_BYTES;
+        uint8_t* pdst = sg + p.off_p + b * SL::PSTAGE_BYTES;
+        // every thread owns up to ITEMS (pixel, 8-channel half) items; all their shared-memory loads are issued before the
+        // first conversion so that the (latency-bound) stage overlaps them
+        constexpr int ITEMS = (HALO_PX * 2 + F_CVT_THREADS - 1) / F_CVT_THREADS;
+        float4 va[ITEMS], vc[ITEMS];
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+          const int item = t + u * F_CVT_THREADS;
+          if (item < HALO_PX * 2) {
+            const int hp = item >> 1, half = item & 1;
+            va[u] = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32);
+            vc[u] = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32 + 16);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+          const int item = t + u * F_CVT_THREADS;
+          if (item < HALO_PX * 2 && p.exp_mode != 2) {
+            const int hp = item >> 1, half = item & 1;
+            uint32_t hi[4], mid[4], lo[4];
+            split3(va[u].x, va[u].y, hi[0], mid[0], lo[0]);
+            split3(va[u].z, va[u].w, hi[1], mid[1], lo[1]);
+            split3(vc[u].x, vc[u].y, hi[2], mid[2], lo[2]);
+            split3(vc[u].z, vc[u].w, hi[3], mid[3], lo[3]);
+            uint8_t* d = pdst + half * SL::K8_BYTES + hp * 16;
+            *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(d + SL::PLANE_BYTES) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            *reinterpret_cast<uint4*>(d + 2 * SL::PLANE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
         fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) { mbar_arrive(pfull(b)); mbar_arrive(fempty(s)); }
-        if (++s == F_FSTAGES) { s = 0; fph ^= 1u; }
+        if (t == 0) ftrace(p, 1, 5, tile);            // converter: planes published
+        if (++s == p.f_stages) { s = 0; fph ^= 1u; }
         if (++b == F_PSTAGES) { b = 0; pph ^= 1u; }
       }
     }
@@ -342,21 +488,57 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const F32Params
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
 template <int TH>
-int launch_th(const CUtensorMap& mx, const F32Params& p, int grid, cudaStream_t st) {
+int launch_th(const CUtensorMap& mx, const CUtensorMap& mr, const CUtensorMap& my, F32Params p, int grid, cudaStream_t st) {
+  using SL = F32Smem<TH>;
   auto kern = conv3x3_f32_tc_kernel<TH>;
-  constexpr int smem = F32Smem<TH>::TOTAL;
-  static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+  // shared-memory plan: bf16 planes (fixed depth), resident kernel, then as many fp32 halo and residual / output stages
+  // as fit (both rings need >= 2)
+  const int w_bytes = 9 * p.cin * p.cout * 2;
+  const int fixed = F_PSTAGES * SL::PSTAGE_BYTES + w_bytes + 3 * F_MAXC * 4 + 512 + 1024 + 3 * 1024;   // + alignment slack
+  const int budget = 232448 - fixed;
+  {
+    p.r_bytes = p.cout == 16 ? 64 * 128 : ceil_div(p.cout, 32) * 128 * 128;   // whole swizzled sub-tiles (Cout = 48: the second is half empty)
   }
-  kern<<<grid, F_THREADS, smem, st>>>(mx, p);
+  p.f_stages = getenv("QNNB_K4_FST") ? atoi(getenv("QNNB_K4_FST")) : 6;
+  p.r_stages = getenv("QNNB_K4_RST") ? atoi(getenv("QNNB_K4_RST")) : 6;
+  if (p.f_stages < 2 || p.f_stages > F_FSTAGES) p.f_stages = 6;
+  if (p.r_stages < 2 || p.r_stages > F_RSTAGES) p.r_stages = 6;
+  p.r_stages &= ~1;                                // even: a buffer always belongs to the same epilogue group
+  while (p.f_stages * SL::F_BYTES + p.r_stages * p.r_bytes > budget) {
+    if (p.r_stages > 2 && p.r_stages * p.r_bytes >= p.f_stages * SL::F_BYTES) p.r_stages -= 2;
+    else if (p.f_stages > 2) --p.f_stages;
+    else if (p.r_stages > 2) p.r_stages -= 2;
+    else { set_error("conv2d: fp32 tensor-core kernel does not fit shared memory (cin=%d cout=%d)", p.cin, p.cout); return QNNB_EINVAL; }
+  }
+  // partial accumulators: as many independent MMA chains as TMEM holds with >= 2 tiles in flight (NP x cout columns each)
+  {
+    p.dbg = get_trace_buffer();
+    p.exp_mode = getenv("QNNB_K4_EXP") ? atoi(getenv("QNNB_K4_EXP")) : 0;
+    int np = 1;
+    if (const char* e = getenv("QNNB_K4_NP")) np = atoi(e) == 3 ? 3 : 1;
+    p.np = np;
+    p.acc_cols = np * p.cout;
+    p.accs = 4 * p.acc_cols <= 512 ? 4 : 2;         // even: each accumulator slot always belongs to the same issuer warp
+  }
+  auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+  p.off_p = up(p.f_stages * SL::F_BYTES, 128);
+  p.off_w = up(p.off_p + F_PSTAGES * SL::PSTAGE_BYTES, 128);
+  p.off_r = up(p.off_w + w_bytes, 1024);
+  p.off_c = p.off_r + p.r_stages * p.r_bytes;
+  p.off_bar = up(p.off_c + 3 * F_MAXC * 4, 16);
+  const int smem = p.off_bar + 512 + 1024;
+  if (smem > 232448) { set_error("conv2d: fp32 tensor-core kernel shared-memory plan overflow (%d B)", smem); return QNNB_EINVAL; }
+  static int configured = 0;                      // largest size this instantiation was configured for
+  if (smem > configured) {
+    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  kern<<<grid, F_THREADS, smem, st>>>(mx, mr, my, p);
   QNNB_CUDA(cudaGetLastError());
   return QNNB_OK;
 }
@@ -381,7 +563,19 @@ int launch_conv_f32_tc(const qnnb_conv_desc& d, const void* x, const void* w, vo
   const int TH = (d.h % 16 == 0) ? 16 : 8;
   const int TN = 16 / TH;
   CUtensorMap mx;
-  {
+  const bool in_merged = d.cin == F_KC;
+  if (in_merged) {
+    // Cin = 16: a pixel IS one 64-byte chunk, so W and C merge into one dimension and the box has 640-byte rows
+    // (10 pixels); the TMA engine's cost is per box row, and 64-byte rows left it the bottleneck of the kernel
+    cuuint64_t dims[3] = {(cuuint64_t)d.cin * d.w, (cuuint64_t)d.n, (cuuint64_t)d.h};
+    cuuint64_t strides[2] = {(cuuint64_t)d.h * d.w * d.cin * 4, (cuuint64_t)d.w * d.cin * 4};
+    cuuint32_t box[3] = {(cuuint32_t)(10 * F_KC), (cuuint32_t)TN, (cuuint32_t)(TH + 2)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(fp32 halo, merged) failed with %d", (int)r); return QNNB_ECUDA; }
+  } else {
     // dimension order (C, W, N, H): the box lands as [row][image][10 px][16 ch]
     cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.n, (cuuint64_t)d.h};
     cuuint64_t strides[3] = {(cuuint64_t)d.cin * 4, (cuuint64_t)d.h * d.w * d.cin * 4, (cuuint64_t)d.w * d.cin * 4};
@@ -392,20 +586,39 @@ int launch_conv_f32_tc(const qnnb_conv_desc& d, const void* x, const void* w, vo
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(fp32 halo) failed with %d", (int)r); return QNNB_ECUDA; }
   }
+  // residual (shortcut) and output tiles: 128-byte rows, SWIZZLE_128B.  Cout >= 32: [pixel][32 channels] sub-tiles;
+  // Cout = 16: the image is viewed as [W/2][32 floats] so that a row holds two pixels
+  const bool two_px = d.cout == 16;
+  CUtensorMap mr, my;
+  memset(&mr, 0, sizeof(mr));
+  for (int which = 0; which < 2; ++which) {
+    void* base = which == 0 ? const_cast<void*>(d.epi.residual) : y;
+    if (which == 0 && d.epi.res_kind != QNNB_KIND_F32) continue;
+    const int wd = two_px ? d.w / 2 : d.w, cd = two_px ? 32 : d.cout;
+    cuuint64_t dims[4] = {(cuuint64_t)cd, (cuuint64_t)wd, (cuuint64_t)d.n, (cuuint64_t)d.h};
+    cuuint64_t strides[3] = {(cuuint64_t)cd * 4, (cuuint64_t)d.h * d.w * d.cout * 4, (cuuint64_t)d.w * d.cout * 4};
+    cuuint32_t box[4] = {32u, two_px ? 4u : 8u, (cuuint32_t)TN, (cuuint32_t)TH};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(which == 0 ? &mr : &my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv2d: cuTensorMapEncodeTiled(fp32 %s) failed with %d", which == 0 ? "residual" : "output", (int)r); return QNNB_ECUDA; }
+  }
   F32Params p;
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
   p.tiles_w = d.w / 8;
   p.tiles_h = d.h / TH;
   p.num_tiles = p.tiles_w * p.tiles_h * ceil_div(d.n, TN);
   p.kchunks = d.cin / F_KC;
+  p.in_merged = in_merged ? 1 : 0;
   p.fd_w = make_fastdiv(p.tiles_w);
   p.fd_h = make_fastdiv(p.tiles_h);
   p.wpk = (const int8_t*)w;
   p.y = (float*)y;
   p.epi = make_epi(d.epi);
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  if (TH == 16) return launch_th<16>(mx, p, grid, st);
-  return launch_th<8>(mx, p, grid, st);
+  if (TH == 16) return launch_th<16>(mx, mr, my, p, grid, st);
+  return launch_th<8>(mx, mr, my, p, grid, st);
 }
 
 }  // namespace qnnb

@@ -1162,6 +1162,7 @@ int launch_conv_tc_v2(const qnnb_conv_desc& d, const void* x, const void* w, voi
 }  // namespace
 
 void set_trace_buffer(unsigned long long* buf, int cap) { g_trace.buf = buf; g_trace.cap = cap; }
+unsigned long long* get_trace_buffer() { return g_trace.buf; }
 
 bool conv_tc_v1_supported(const qnnb_conv_desc& d) {
   Geometry g;

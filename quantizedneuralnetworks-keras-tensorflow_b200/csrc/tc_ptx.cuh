@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define QNNB_STR2(x) #x
+#define QNNB_STR(x) QNNB_STR2(x)
+
 namespace qnnb {
 namespace tcx {
 
@@ -44,7 +47,11 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifdef QNNB_PARK_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, " QNNB_STR(QNNB_PARK_NS) ";\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 20000;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -61,6 +68,13 @@ __device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
   asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// one lane of the (fully active) warp; the compiler knows an elect.sync region is single-threaded, so warp-uniform
+// instructions inside it (tcgen05.mma, tcgen05.commit, TMA) are emitted without a per-instruction election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -74,6 +88,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
