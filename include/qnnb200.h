@@ -106,6 +106,9 @@ typedef struct qnnb_dense_desc {
   int32_t in_kind;          /* QNNB_KIND_I8 | B1 | F32 */
   int32_t softmax;          /* 1: y = softmax(z) and, if logits != NULL, logits = z */
   qnnb_epilogue epi;        /* act must be QNNB_ACT_NONE, pool 0, no residual */
+  int32_t avg_positions;    /* 0 | 1: plain.  P > 1 (fp32 input only): x is [n][P][fin] and the layer sees the SUM over the P
+                               positions -- AveragePooling2D(8) + Flatten of models/resnet.py:134-135 folded in; acc_scale
+                               carries the 1/P */
 } qnnb_dense_desc;
 
 int         qnnb_version(void);

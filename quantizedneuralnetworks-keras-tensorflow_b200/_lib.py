@@ -56,6 +56,7 @@ class DenseDesc(C.Structure):
         ("in_kind", C.c_int32),
         ("softmax", C.c_int32),
         ("epi", Epilogue),
+        ("avg_positions", C.c_int32),
     ]
 
 

@@ -144,6 +144,8 @@ int qnnb_dense(const qnnb_dense_desc* d, const void* x, const void* w, float* y,
   int rc = validate_epilogue(d->epi, false, false);
   if (rc) return rc;
   QNNB_CHECK_ARG(d->epi.act == QNNB_ACT_NONE, "dense: fused activation not supported (act=%d)", d->epi.act);
+  QNNB_CHECK_ARG(d->avg_positions >= 0 && (d->avg_positions <= 1 || d->in_kind == QNNB_KIND_F32),
+                 "dense: avg_positions=%d needs fp32 input", d->avg_positions);
   if (d->n == 0) return QNNB_OK;
   return launch_dense(*d, x, w, y, logits, (cudaStream_t)stream);
 }

@@ -8,9 +8,10 @@
 //   BinaryConv2D.call    layers/binary_layers.py:160-187
 //   TernaryConv2D.call   layers/ternary_layers.py:156-174
 //
-// Tiling: one CTA = 8x8 output pixels of one image x 64 output channels; 256 threads, thread
+// Tiling: one CTA = TPY x TPX output pixels of one image x TC output channels; 256 threads, thread
 // (ty, tx) owns the 2x2 pixel window ty and the 4 consecutive channels 4*tx..4*tx+3, so the
-// 2x2 max-pool is an in-register reduction.  K is streamed through shared memory in chunks of
+// 2x2 max-pool is an in-register reduction.  Three shapes keep all 256 threads busy on narrow
+// layers: 8x8 px x 64 ch, 8x16 px x 32 ch (Cout <= 32), 16x16 px x 16 ch (Cout <= 16).  K is streamed through shared memory in chunks of
 // CKW words per tap (a word = 4 int8 channels, 32 binary channels or 1 float channel).
 // Because every epilogue step is monotone in the accumulator for a fixed channel, pooling is
 // done on the raw accumulators (max, or min when the BN slope is negative) BEFORE the fp32
@@ -21,11 +22,19 @@ namespace qnnb {
 
 namespace {
 
-constexpr int TP = 8;
-constexpr int TC = 64;
 constexpr int CKW = 8;
 constexpr int MAXK = 3;
-constexpr int MAX_I = (TP - 1) * 2 + MAXK;   // 17: halo extent under stride 2
+
+// tile shape for a channel tile of TC: (TC / 4) channel quads x (256 / (TC / 4)) pixel windows
+template <int TC> struct Tile {
+  static constexpr int NQ = TC / 4;                         // threads along the channel axis
+  static constexpr int WIN = 256 / NQ;                      // 2x2 pixel windows per CTA
+  static constexpr int WX = (TC == 64) ? 4 : 8;             // windows per row
+  static constexpr int WY = WIN / WX;
+  static constexpr int TPX = 2 * WX, TPY = 2 * WY;          // output pixels per CTA
+  static constexpr int MAX_IX = (TPX - 1) * 2 + MAXK;       // halo extent under stride 2
+  static constexpr int MAX_IY = (TPY - 1) * 2 + MAXK;
+};
 
 struct ConvP {
   int n, h, w, cin, cout, kh, kw, stride, pad_t, pad_l, oh, ow;
@@ -47,31 +56,33 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
 template <int KIND> struct AccT { typedef int type; };
 template <> struct AccT<QNNB_KIND_F32> { typedef float type; };
 
-template <int KIND>
+template <int KIND, int TC>
 __global__ void __launch_bounds__(256)
 conv_generic_kernel(const ConvP p) {
   typedef typename AccT<KIND>::type acc_t;
-  __shared__ uint32_t sa[MAX_I * MAX_I * CKW];
+  typedef Tile<TC> T;
+  constexpr int TPX = T::TPX, TPY = T::TPY;
+  __shared__ uint32_t sa[T::MAX_IY * T::MAX_IX * CKW];
   __shared__ __align__(16) uint32_t sw[MAXK * MAXK * CKW * TC];
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15;
-  const int ty = tid >> 4;
-  const int wy = ty >> 2, wx = ty & 3;
+  const int tx = tid % T::NQ;
+  const int ty = tid / T::NQ;
+  const int wy = ty / T::WX, wx = ty % T::WX;
 
   int tile = blockIdx.x;
   const int tile_x = tile % p.tiles_x; tile /= p.tiles_x;
   const int tile_y = tile % p.tiles_y; tile /= p.tiles_y;
   const int img = tile;
-  const int oy0 = tile_y * TP, ox0 = tile_x * TP;
+  const int oy0 = tile_y * TPY, ox0 = tile_x * TPX;
   const int c_base = blockIdx.y * TC;
   const int taps = p.kh * p.kw;
 
   // halo origin / extent in input coordinates
   const int iy0 = oy0 * p.stride - p.pad_t;
   const int ix0 = ox0 * p.stride - p.pad_l;
-  const int IH = (TP - 1) * p.stride + p.kh;
-  const int IW = (TP - 1) * p.stride + p.kw;
+  const int IH = (TPY - 1) * p.stride + p.kh;
+  const int IW = (TPX - 1) * p.stride + p.kw;
 
   acc_t acc[4][4];
 #pragma unroll
@@ -271,8 +282,10 @@ int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, v
   p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout; p.kh = d.kh; p.kw = d.kw; p.stride = d.stride;
   same_pad(d.h, d.kh, d.stride, &p.oh, &p.pad_t);
   same_pad(d.w, d.kw, d.stride, &p.ow, &p.pad_l);
-  p.tiles_y = ceil_div(p.oh, TP);
-  p.tiles_x = ceil_div(p.ow, TP);
+  // channel tile: the widest one that does not leave most threads idle (the bit-packing epilogue needs >= 32 channels)
+  const int tc = (d.cout <= 16 && d.epi.act != QNNB_ACT_SIGN) ? 16 : (d.cout <= 32 ? 32 : 64);
+  p.tiles_y = ceil_div(p.oh, tc == 16 ? Tile<16>::TPY : (tc == 32 ? Tile<32>::TPY : Tile<64>::TPY));
+  p.tiles_x = ceil_div(p.ow, tc == 16 ? Tile<16>::TPX : (tc == 32 ? Tile<32>::TPX : Tile<64>::TPX));
   p.cin_pad = (d.cin + 3) / 4 * 4;
   if (d.in_kind == QNNB_KIND_F32) p.kwords = d.cin;
   else if (d.in_kind == QNNB_KIND_B1) p.kwords = (d.cin + 31) / 32;
@@ -281,14 +294,21 @@ int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, v
   p.epi = make_epi(d.epi);
   long long gx = (long long)d.n * p.tiles_y * p.tiles_x;
   QNNB_CHECK_ARG(gx > 0 && gx < 2147483647LL, "conv2d: grid too large");
-  dim3 grid((unsigned)gx, (unsigned)ceil_div(d.cout, TC));
+  dim3 grid((unsigned)gx, (unsigned)ceil_div(d.cout, tc));
+#define QNNB_GENERIC_LAUNCH(KIND)                                                          \
+  do {                                                                                     \
+    if (tc == 16) conv_generic_kernel<KIND, 16><<<grid, 256, 0, st>>>(p);                  \
+    else if (tc == 32) conv_generic_kernel<KIND, 32><<<grid, 256, 0, st>>>(p);             \
+    else conv_generic_kernel<KIND, 64><<<grid, 256, 0, st>>>(p);                           \
+  } while (0)
   switch (d.in_kind) {
-    case QNNB_KIND_U8: conv_generic_kernel<QNNB_KIND_U8><<<grid, 256, 0, st>>>(p); break;
-    case QNNB_KIND_I8: conv_generic_kernel<QNNB_KIND_I8><<<grid, 256, 0, st>>>(p); break;
-    case QNNB_KIND_B1: conv_generic_kernel<QNNB_KIND_B1><<<grid, 256, 0, st>>>(p); break;
-    case QNNB_KIND_F32: conv_generic_kernel<QNNB_KIND_F32><<<grid, 256, 0, st>>>(p); break;
+    case QNNB_KIND_U8: QNNB_GENERIC_LAUNCH(QNNB_KIND_U8); break;
+    case QNNB_KIND_I8: QNNB_GENERIC_LAUNCH(QNNB_KIND_I8); break;
+    case QNNB_KIND_B1: QNNB_GENERIC_LAUNCH(QNNB_KIND_B1); break;
+    case QNNB_KIND_F32: QNNB_GENERIC_LAUNCH(QNNB_KIND_F32); break;
     default: set_error("conv2d: bad in_kind %d", d.in_kind); return QNNB_EINVAL;
   }
+#undef QNNB_GENERIC_LAUNCH
   QNNB_CUDA(cudaGetLastError());
   return QNNB_OK;
 }

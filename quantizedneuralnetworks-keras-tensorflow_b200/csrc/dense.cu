@@ -199,6 +199,63 @@ dense_smem_kernel(const DenseP p) {
   }
 }
 
+// Global average pooling + dense on fp32 maps (models/resnet.py:134-140): one warp per image sums the P positions
+// per channel (coalesced 128-byte rows, eight independent loads in flight), then takes the [units][fin] dot products.
+// HBM-bound: reads P * fin floats per image exactly once.
+__global__ void __launch_bounds__(256)
+dense_avgpool_f32_kernel(const DenseP p, int positions) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int MAXJ = 8;                                    // fin <= 256
+  const int nj = (p.fin + 31) / 32;
+  const bool active = lane < p.units;
+  const ChanConst cc = load_chan(p.epi, lane, active);
+  for (int img = blockIdx.x * 8 + warp; img < p.n; img += gridDim.x * 8) {
+    float s[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) s[j] = 0.f;
+    const float* xr = (const float*)p.x + (long long)img * positions * p.fin;
+    for (int pos0 = 0; pos0 < positions; pos0 += 8) {
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        if (j < nj) {
+          const int c = lane + 32 * j;
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (c < p.fin && pos0 + q < positions) ? __ldg(xr + (long long)(pos0 + q) * p.fin + c) : 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s[j] += v[q];
+        }
+      }
+    }
+    float z = 0.f;
+    for (int u = 0; u < p.units; ++u) {
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int c = lane + 32 * j;
+        if (j < nj && c < p.fin) part = fmaf(s[j], (float)__ldg((const int8_t*)p.w + (long long)u * p.fin_pad + c), part);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == u) z = part;
+    }
+    z = affine(z, cc);
+    if (p.softmax) {
+      if (active && p.logits) p.logits[(long long)img * p.units + lane] = z;
+      float m = active ? z : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float ex = active ? expf(z - m) : 0.f;
+      float sum = ex;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      z = ex / sum;
+    }
+    if (active) p.y[(long long)img * p.units + lane] = z;
+  }
+}
+
 }  // namespace
 
 int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st) {
@@ -213,6 +270,13 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
   p.epi = make_epi(d.epi);
   int blocks = ceil_div(d.n, 8);
   if (blocks < 1) blocks = 1;
+  if (d.avg_positions > 1) {
+    QNNB_CHECK_ARG(d.in_kind == QNNB_KIND_F32 && d.fin <= 256, "dense: avg_positions needs fp32 input with fin <= 256 (got kind %d, fin %d)", d.in_kind, d.fin);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dense_avgpool_f32_kernel<<<blocks, 256, 0, st>>>(p, d.avg_positions);
+    QNNB_CUDA(cudaGetLastError());
+    return QNNB_OK;
+  }
   const size_t wbytes = (size_t)d.units * p.kwords * 4;
   if (d.in_kind != QNNB_KIND_F32 && d.units <= UG && (p.kwords & 3) == 0 && wbytes <= 160 * 1024) {
     int fb = blocks > 148 * 2 ? 148 * 2 : blocks;

@@ -156,10 +156,17 @@ def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epil
 
 
 def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=False, want_logits=False,
-          out: torch.Tensor | None = None, logits: torch.Tensor | None = None):
+          out: torch.Tensor | None = None, logits: torch.Tensor | None = None, avg_positions=0):
+    """``avg_positions`` = P > 1 (fp32 input): ``x`` is [n, P*fin] laid out [n][P][fin]; the layer input is the sum over
+    the P positions (global average pooling folded in, the 1/P is part of ``epi.acc_scale``)."""
     n = int(x.data.shape[0])
     fin = int(np.prod(x.shape[1:]))
     d = L.DenseDesc()
+    if avg_positions and avg_positions > 1:
+        if fin % int(avg_positions):
+            raise ValueError("dense: %d features do not split into %d positions" % (fin, avg_positions))
+        fin //= int(avg_positions)
+        d.avg_positions = int(avg_positions)
     d.n, d.fin, d.units = n, fin, int(units)
     d.in_kind = KIND_CODE[x.kind]
     d.softmax = 1 if softmax else 0

@@ -240,7 +240,14 @@ class Plan:
         # pack the (in, units) kernel; under global average pooling the kernel has `ch` rows and is
         # replicated over the pooled pixels
         rows = lay.kernel.shape[0]
-        if pool > 1:
+        avg_positions = 0
+        if pool > 1 and x.kind == "f32" and ch <= 256:
+            # fp32 maps: the kernel sums the pooled positions itself (one pass over x, a [units][ch] kernel)
+            if rows != ch or fin != pool * ch:
+                raise ValueError("plan: dense kernel %s does not match pooled features %d" % (lay.kernel.shape, ch))
+            wp = lay.packed_kernel(dev, wfmt)
+            avg_positions = pool
+        elif pool > 1:
             if rows != ch or fin != pool * ch:
                 raise ValueError("plan: dense kernel %s does not match pooled features %d" % (lay.kernel.shape, ch))
             key = "pool%d" % pool
@@ -261,7 +268,7 @@ class Plan:
             inv, shift = self._bn_dev(st, st.bn, dev)
         epi = K.make_epilogue(scale, bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift)
         xin = K.QTensor(x.kind, x.data.reshape(n, -1), x.scale, fin if x.kind != "b1" else fin)
-        out, logits = K.dense(xin, wp, lay.units, epi, softmax=st.softmax, want_logits=st.softmax)
+        out, logits = K.dense(xin, wp, lay.units, epi, softmax=st.softmax, want_logits=st.softmax, avg_positions=avg_positions)
         env[st.out] = K.QTensor("f32", out, 1.0, lay.units)
         if logits is not None:
             env["logits"] = logits
