@@ -298,7 +298,11 @@ def run_ours(args):
     # ---- parity spot-check of the benchmarked configuration against the exact oracle (small slice)
     from oracle import exact
     xs = host[0][:8].numpy()
-    ok = bool(np.array_equal(model.predict(xs, impl=impl), exact.forward(nodes, xs)))
+    got_s, want_s = model.predict(xs, impl=impl), exact.forward(nodes, xs)
+    if cf.network_type in ("full-qnn", "full-bnn", "qbnn", "qtnn"):
+        ok = bool(np.array_equal(got_s, want_s))                      # integer paths: bit-exact
+    else:                                                             # fp32 activations: north_star tolerance
+        ok = bool(np.abs(got_s - want_s).max() <= 1e-4 * max(float(np.abs(want_s).max()), 1e-30))
 
     # ---- CUDA graphs: one per input buffer.  Consecutive steps are independent batches, so they are replayed
     # round-robin on NS streams (graph i always on stream i % NS, with that stream's private memory pool): the
