@@ -443,7 +443,7 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
@@ -465,7 +465,7 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, true, true);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -601,7 +601,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 
   if (warp == 0) {
     // ===================== halo producer: one box per (tile, channel chunk) =====================
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       int hb = 0; uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int mt, n0, h0, w0;
@@ -616,7 +616,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     }
   } else if (warp == 3) {
     // ===================== weight producer: one {KC, 128} box per (tile, chunk, tap) =====================
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int mt = tile - fdiv(tile, p.fd_m) * p.m_tiles;
@@ -637,7 +637,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     // tcgen05.mma issue is itself blocking, so nine such waits per chunk in the MMA issuer left the tensor pipe idle
     // ~30 % of the time (cycle accounting, profiles/).  This otherwise idle thread absorbs the waits and publishes a
     // running count of landed weight stages; the issuer only polls that word (one shared-memory load).
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       int as = 0; uint32_t aphase = 0, count = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int ks = 0; ks < 9 * p.kchunks; ++ks) {
@@ -650,7 +650,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #endif
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, true, true);
       uint32_t a_need = 0, a_seen = 0;
       (void)a_need; (void)a_seen;
@@ -831,7 +831,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
 
   if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, /*a signed*/ true, /*b unsigned*/ false);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
