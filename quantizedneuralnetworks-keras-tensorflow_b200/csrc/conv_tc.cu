@@ -180,16 +180,13 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
       else qc = make_qconst<FOLD>(e, ch, ch_ok);
     }
     // Pooling picks max(acc) where the channel's map is increasing and min(acc) where it is decreasing (BN slope
-    // < 0).  min(x) = -max(-x), so instead of computing both extrema and selecting (5 ALU-pipe ops per output) the
-    // raw accumulators are multiplied by sg = +-1 (IMAD: FMA pipe) before ONE max reduction, and the sign is undone
-    // exactly inside the constants: negation commutes with every RN op.  qp = constants for the pooled path.
+    // < 0).  The integer min/max instruction takes the choice as a predicate operand, so selecting per 2-/3-input
+    // step (pick2 / pick3 below) costs ONE reduction tree -- not both extrema plus a select.
     const bool dec = qc.b < 0.f;
-    const int sg = dec ? -1 : 1;
-    QConst qp = qc;
-    if (dec) {
-      if constexpr (FOLD) { qp.a = -qc.a; qp.b = -qc.b; }     // ((sg*f + sg*a) * (sg*b)) + c
-      else qp.s = -qc.s;                                        // (sg*f) * (sg*s)
-    }
+    auto pick4 = [dec](int a, int b, int c, int d) {
+      const int lo = dec ? min(a, b) : max(a, b);
+      return dec ? min(min(c, d), lo) : max(max(c, d), lo);
+    };
     const int pitch = PITCH ? PITCH : p.out_pitch;
     const float qm = e.qm;
     const int acc = it & 1;
@@ -235,8 +232,8 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
               for (int pc = 0; pc < 4; ++pc) {
                 const int i00 = ((2 * pr) * TN + img) * 8 + 2 * pc;
                 constexpr int VS = TN * 8;             // columns between vertically adjacent pixels
-                const int mx = max(max(v[i00] * sg, v[i00 + 1] * sg), max(v[i00 + VS] * sg, v[i00 + VS + 1] * sg));
-                srow[((pr * TN + img) * 4 + pc) * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qp), qm);
+                const int mx = pick4(v[i00], v[i00 + 1], v[i00 + VS], v[i00 + VS + 1]);
+                srow[((pr * TN + img) * 4 + pc) * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qc), qm);
               }
             }
           }
@@ -271,8 +268,8 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
 #pragma unroll
           for (int pc = 0; pc < PC; ++pc) {
             const int i00 = (2 * pr) * TW + 2 * pc;
-            const int mx = max(max(v[i00] * sg, v[i00 + 1] * sg), max(v[i00 + TW] * sg, v[i00 + TW + 1] * sg));
-            srow[(pr * PC + pc) * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qp), qm);
+            const int mx = pick4(v[i00], v[i00 + 1], v[i00 + TW], v[i00 + TW + 1]);
+            srow[(pr * PC + pc) * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qc), qm);
           }
         }
       } else {

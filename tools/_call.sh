@@ -1,13 +1,10 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s22_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s22_tests.log
-tail -4 gpurun_out/s22_tests.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s24_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s24_tests.log
+tail -3 gpurun_out/s24_tests.log
 for rep in 1 2; do
-timeout 300 python bench.py --workload cfg3 --streams 1 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/s22_cfg3_$rep.log 2>&1
+timeout 300 python bench.py --workload cfg3 --streams 1 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/s24_cfg3_$rep.log 2>&1
 done
-timeout 300 python bench.py --workload cfg3 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/s22_cfg3_4s.log 2>&1
-timeout 300 python bench.py --workload cfg4 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/s22_cfg4.log 2>&1
-timeout 300 python bench.py --workload cfg2 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/s22_cfg2.log 2>&1
-grep -h value gpurun_out/s22_cfg*.log | python -c "
+grep -h value gpurun_out/s24_cfg*.log | python -c "
 import sys,json
 for l in sys.stdin:
-    d=json.loads(l); r=d['roofline']; print(d['config']['workload'][:5], d['config']['streams'], round(d['value']), round(d['e2e']['value']), d['config']['parity_vs_exact_oracle'], d['clocks']['reasons'], {k:round(v*1e3,1) for k,v in r['per_kernel_ms'].items()})
+    d=json.loads(l); r=d['roofline']; print(d['config']['workload'][:5], d['config']['streams'], round(d['value']), round(d['e2e']['value']), d['config']['parity_vs_exact_oracle'], {k:round(v*1e3,1) for k,v in r['per_kernel_ms'].items()})
 "
