@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/qnnb200.h"
 
@@ -82,6 +83,30 @@ static inline bool is_pow2_scale(float x) {
 }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Consecutive layers are separate kernels on one stream.  Every kernel of the path (a) lets the NEXT kernel's CTAs
+// start as soon as SM resources free up (launch_dependents at entry) and (b) runs its own prologue -- barrier init,
+// TMEM allocation, tensor-map prefetch, staging of the layer's kernel weights, none of which depends on the previous
+// layer -- before griddepcontrol.wait, which returns once the previous kernel has completed and its writes are
+// visible.  Launch latency and prologue of layer L+1 thus overlap the tail of layer L.  Without the launch attribute
+// (QNNB_PDL=0) both instructions are no-ops.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Kernel launch with the programmatic-stream-serialization attribute (captured as a programmatic edge in CUDA graphs).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("QNNB_PDL"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Per-channel constants of the affine part (steps 1-3 of the fixed order).
 struct ChanConst {
   float scale, bias, inv, shift;

@@ -181,6 +181,7 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const int cout = p.cout;
   const int kchunks = p.kchunks;
 
+  if (threadIdx.x == 0) griddep_launch_dependents();
   // ---- resident kernel: bf16, [(tap, chunk, 8-ch half)][cout][16 B] (un-swizzled K-major core matrices)
   {
     const int items = 9 * kchunks * 2 * cout;
@@ -228,6 +229,7 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  griddep_wait();                        // activations / shortcut / output buffers only after the previous kernel completed
 
   auto decode = [&](int tile, int& n0, int& h0, int& w0) {
     const int q = fdiv(tile, p.fd_w);
@@ -538,8 +540,7 @@ int launch_th(const CUtensorMap& mx, const CUtensorMap& mr, const CUtensorMap& m
     QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  kern<<<grid, F_THREADS, smem, st>>>(mx, mr, my, p);
-  QNNB_CUDA(cudaGetLastError());
+  QNNB_CUDA(launch_pdl(kern, dim3(grid), dim3(F_THREADS), (size_t)smem, st, mx, mr, my, p));
   return QNNB_OK;
 }
 

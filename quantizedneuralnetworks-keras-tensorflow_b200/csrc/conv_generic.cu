@@ -62,6 +62,8 @@ conv_generic_kernel(const ConvP p) {
   typedef typename AccT<KIND>::type acc_t;
   typedef Tile<TC> T;
   constexpr int TPX = T::TPX, TPY = T::TPY;
+  if (threadIdx.x == 0) griddep_launch_dependents();
+  griddep_wait();
   __shared__ uint32_t sa[T::MAX_IY * T::MAX_IX * CKW];
   __shared__ __align__(16) uint32_t sw[MAXK * MAXK * CKW * TC];
 
@@ -297,9 +299,11 @@ int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, v
   dim3 grid((unsigned)gx, (unsigned)ceil_div(d.cout, tc));
 #define QNNB_GENERIC_LAUNCH(KIND)                                                          \
   do {                                                                                     \
-    if (tc == 16) conv_generic_kernel<KIND, 16><<<grid, 256, 0, st>>>(p);                  \
-    else if (tc == 32) conv_generic_kernel<KIND, 32><<<grid, 256, 0, st>>>(p);             \
-    else conv_generic_kernel<KIND, 64><<<grid, 256, 0, st>>>(p);                           \
+    cudaError_t e__;                                                                       \
+    if (tc == 16) e__ = launch_pdl(conv_generic_kernel<KIND, 16>, grid, dim3(256), (size_t)0, st, p);      \
+    else if (tc == 32) e__ = launch_pdl(conv_generic_kernel<KIND, 32>, grid, dim3(256), (size_t)0, st, p); \
+    else e__ = launch_pdl(conv_generic_kernel<KIND, 64>, grid, dim3(256), (size_t)0, st, p);               \
+    if (e__ != cudaSuccess) return cuda_fail(e__, "conv_generic launch");                  \
   } while (0)
   switch (d.in_kind) {
     case QNNB_KIND_U8: QNNB_GENERIC_LAUNCH(QNNB_KIND_U8); break;

@@ -563,6 +563,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AS + 2 * HB + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * AS + 2 * HB + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SL::BAR_OFFSET + 8 * (2 * AS + 2 * HB + 4));
+  if (threadIdx.x == 0) griddep_launch_dependents();
   // weight stages made ready so far (monotonic): written by the watcher thread, polled by the MMA issuer
   const uint32_t a_ready = tmem_slot + 8u;
   if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_gen + SL::BAR_OFFSET + 8 * (2 * AS + 2 * HB + 4) + 8) = 0u;
@@ -599,6 +600,8 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   if (warp == 0) {
     // ===================== halo producer: one box per (tile, channel chunk) =====================
     if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
+      griddep_wait();                                // the previous layer's output is complete and visible from here on;
+                                                     // the weight ring (warp 3) starts filling before that
       int hb = 0; uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int mt, n0, h0, w0;
@@ -706,6 +709,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #endif
     }
   } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
+    griddep_wait();                                  // (its stores follow the halo loads anyway; this makes it explicit)
     epilogue_role_n<8, POOL, OUT_F32, /*FOLD*/ true, /*PITCH*/ TILE_M, 1, TH, SL::NSTG, true, /*ILV*/ true, SIGN, SL::SPLIT>(
         p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0), smem_gen + SL::STG_OFFSET, SL::STG_BYTES, warp, lane);
   }
@@ -776,6 +780,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 0) griddep_launch_dependents();
   // resident A tile(s): 16-byte K chunk j of row m; G = 1: row = channel, chunks 0..2 = packed words 0..8;
   // G = 2: row 64 g + c holds channel c's words in chunks 4g..4g+2 and zeros elsewhere (block diagonal)
   {
@@ -825,6 +830,7 @@ conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  griddep_wait();                        // input images / output buffer only after the previous kernel has completed
 
   if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -1027,8 +1033,7 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
   }
   auto go = [&](auto kern, int smem) -> int {
     QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, K5_THREADS, smem, st>>>((const uint8_t*)x, (const int8_t*)w, my, p);
-    QNNB_CUDA(cudaGetLastError());
+    QNNB_CUDA(launch_pdl(kern, dim3(grid), dim3(K5_THREADS), (size_t)smem, st, (const uint8_t*)x, (const int8_t*)w, my, p));
     return QNNB_OK;
   };
   if (f32) return go(conv3x3_u8c3_tc_kernel<false, true, 0, 1>, K5Smem<false, true, 1>::TOTAL);
@@ -1067,8 +1072,7 @@ int launch_v2_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtens
     QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, smem, st>>>(mw, mx, my, p);
-  QNNB_CUDA(cudaGetLastError());
+  QNNB_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)smem, st, mw, mx, my, p));
   return QNNB_OK;
 }
 

@@ -118,6 +118,7 @@ dense_smem_kernel(const DenseP p) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    griddep_launch_dependents();
     const uint32_t bytes = (uint32_t)(p.units * kvec) * 16u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     constexpr uint32_t CH = 16384;
@@ -133,6 +134,7 @@ dense_smem_kernel(const DenseP p) {
   const ChanConst cc = load_chan(p.epi, lane, active);
   constexpr int XB = 8;
   bool weights_ready = false;
+  griddep_wait();                        // x is the previous layer's output; the kernel weights above are not
   for (int img = blockIdx.x * 8 + warp; img < p.n; img += gridDim.x * 8) {
     int acc[UG];
 #pragma unroll
@@ -204,6 +206,8 @@ dense_smem_kernel(const DenseP p) {
 // HBM-bound: reads P * fin floats per image exactly once.
 __global__ void __launch_bounds__(256)
 dense_avgpool_f32_kernel(const DenseP p, int positions) {
+  if (threadIdx.x == 0) griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   constexpr int MAXJ = 8;                                    // fin <= 256
@@ -273,8 +277,7 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
   if (d.avg_positions > 1) {
     QNNB_CHECK_ARG(d.in_kind == QNNB_KIND_F32 && d.fin <= 256, "dense: avg_positions needs fp32 input with fin <= 256 (got kind %d, fin %d)", d.in_kind, d.fin);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    dense_avgpool_f32_kernel<<<blocks, 256, 0, st>>>(p, d.avg_positions);
-    QNNB_CUDA(cudaGetLastError());
+    QNNB_CUDA(launch_pdl(dense_avgpool_f32_kernel, dim3(blocks), dim3(256), (size_t)0, st, p, (int)d.avg_positions));
     return QNNB_OK;
   }
   const size_t wbytes = (size_t)d.units * p.kwords * 4;
@@ -282,10 +285,10 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
     int fb = blocks > 148 * 2 ? 148 * 2 : blocks;
     if (d.in_kind == QNNB_KIND_I8) {
       QNNB_CUDA(cudaFuncSetAttribute(dense_smem_kernel<QNNB_KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
-      dense_smem_kernel<QNNB_KIND_I8><<<fb, 256, wbytes, st>>>(p);
+      QNNB_CUDA(launch_pdl(dense_smem_kernel<QNNB_KIND_I8>, dim3(fb), dim3(256), wbytes, st, p));
     } else {
       QNNB_CUDA(cudaFuncSetAttribute(dense_smem_kernel<QNNB_KIND_B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
-      dense_smem_kernel<QNNB_KIND_B1><<<fb, 256, wbytes, st>>>(p);
+      QNNB_CUDA(launch_pdl(dense_smem_kernel<QNNB_KIND_B1>, dim3(fb), dim3(256), wbytes, st, p));
     }
     QNNB_CUDA(cudaGetLastError());
     return QNNB_OK;

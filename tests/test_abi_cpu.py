@@ -39,7 +39,7 @@ def test_struct_layout_matches_header_constants():
     src = open(HEADER).read()
     for name, val in [("QNNB_KIND_U8", L.KIND_U8), ("QNNB_KIND_I8", L.KIND_I8), ("QNNB_KIND_B1", L.KIND_B1),
                       ("QNNB_KIND_F32", L.KIND_F32), ("QNNB_ACT_QUANT", L.ACT_QUANT), ("QNNB_ACT_SIGN", L.ACT_SIGN),
-                      ("QNNB_ACT_LEAKY", L.ACT_LEAKY), ("QNNB_W_TERNARY", L.W_TERNARY), ("QNNB_WFMT_B1", L.WFMT_B1),
+                      ("QNNB_ACT_LEAKY", L.ACT_LEAKY), ("QNNB_ACT_SIGN_I8", L.ACT_SIGN_I8), ("QNNB_W_TERNARY", L.W_TERNARY), ("QNNB_WFMT_B1", L.WFMT_B1),
                       ("QNNB_IMPL_TCGEN05", L.IMPL_TCGEN05)]:
         m = re.search(r"#define\s+%s\s+(-?\d+)" % name, src)
         assert m and int(m.group(1)) == val, name
@@ -56,9 +56,9 @@ def test_struct_layout_matches_header_constants():
 #include <stddef.h>
 #include "qnnb200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(qnnb_epilogue), sizeof(qnnb_conv_desc), sizeof(qnnb_dense_desc),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(qnnb_epilogue), sizeof(qnnb_conv_desc), sizeof(qnnb_dense_desc),
          offsetof(qnnb_conv_desc, epi), offsetof(qnnb_dense_desc, epi), offsetof(qnnb_epilogue, residual),
-         offsetof(qnnb_epilogue, pool));
+         offsetof(qnnb_epilogue, pool), offsetof(qnnb_dense_desc, avg_positions));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -66,7 +66,7 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), "-o", os.path.join(td, "t"), os.path.join(td, "t.c")])
         got = [int(v) for v in subprocess.check_output([os.path.join(td, "t")]).split()]
     want = [C.sizeof(L.Epilogue), C.sizeof(L.ConvDesc), C.sizeof(L.DenseDesc), L.ConvDesc.epi.offset,
-            L.DenseDesc.epi.offset, L.Epilogue.residual.offset, L.Epilogue.pool.offset]
+            L.DenseDesc.epi.offset, L.Epilogue.residual.offset, L.Epilogue.pool.offset, L.DenseDesc.avg_positions.offset]
     assert got == want
 
 

@@ -525,3 +525,27 @@ def test_conv2d_f32_tcgen05_tolerance(case):
     # and it agrees with the CUDA-core kernel to the same tolerance
     y2 = K.conv2d(xq, wp, 3, 3, cout, 1, epi, impl=L.IMPL_GENERIC).data.cpu().numpy()
     assert np.abs(got - y2).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n,pos,ch,units,softmax", [(5, 64, 64, 10, True), (3, 16, 96, 7, False), (40, 64, 64, 10, True)])
+def test_dense_with_global_average_pool_fp32(n, pos, ch, units, softmax):
+    """AveragePooling2D + Flatten + Dense on an fp32 map as ONE launch (qnnb_dense_desc.avg_positions): tolerance class
+    of the fp32 path, against float64."""
+    q, L, K = _mods()
+    rng = np.random.default_rng(_seed(("avgdense", n, pos, ch, units)))
+    x = rng.normal(0, 1, size=(n, pos, ch)).astype(F32)
+    kernel = rng.uniform(-1, 1, size=(ch, units)).astype(F32)
+    lv = exact.quantize_levels(kernel.reshape(1, 1, ch, units), 4).reshape(ch, units).astype(np.float64) / 8.0
+    z = (x.astype(np.float64).sum(axis=1) / pos) @ lv
+    want = z
+    if softmax:
+        e = np.exp(z - z.max(axis=1, keepdims=True))
+        want = e / e.sum(axis=1, keepdims=True)
+    wp = K.pack_weights(dev(kernel), L.W_QUANT, 4, 1.0, L.WFMT_I8)
+    epi = K.make_epilogue(K.acc_scale(1.0 / pos, 1.0 / 8))
+    out, logits = K.dense(K.QTensor("f32", dev(x.reshape(n, -1)), 1.0, pos * ch), wp, units, epi, softmax=softmax,
+                          want_logits=softmax, avg_positions=pos)
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
+    if softmax:
+        assert np.abs(logits.cpu().numpy() - z).max() <= 1e-5 * np.abs(z).max()
