@@ -618,10 +618,15 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     // ===================== weight producer: one {KC, 128} box per (tile, chunk, tap) =====================
     if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       int as = 0; uint32_t aphase = 0;
+      int issued = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int mt = tile - fdiv(tile, p.fd_m) * p.m_tiles;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
+            // the ring is filled once ahead of the previous kernel's completion (PDL); any wait that can actually block
+            // happens after it, so the spin limit in mbar_wait never measures another kernel's run time
+            if (issued == AS) griddep_wait();
+            ++issued;
             mbar_wait(aempty(as), aphase ^ 1u);
             mbar_expect_tx(afull(as), SL::A_BYTES);
             tma_load_2d(smem_base + SL::A_OFFSET + as * SL::A_BYTES, &map_w, afull(as), tap * p.cin + kc * KC, mt * TILE_M);
@@ -652,6 +657,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     // ===================== MMA issuer =====================
     if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, true, true);
+      griddep_wait();                                // no global access here: turns the first halo wait into a hardware wait
       uint32_t a_need = 0, a_seen = 0;
       (void)a_need; (void)a_seen;
       // B view: rows of KC bytes, 8-row groups one halo row (10 pixels) apart
