@@ -8,7 +8,7 @@
 // (SURVEY.md 8d, config 5), so the job of the kernel is to stream activations once at memory speed.
 //
 // Arithmetic.  The kernel levels are exact in bf16; an fp32 activation is split EXACTLY into three bf16 terms
-// x = hi + mid + lo (8 mantissa bits each), so  sum x*w = sum hi*w + sum mid*w + sum lo*w  is three bf16 MMAs whose
+// x = hi + mid + lo (8 significant bits each, by truncation), so  sum x*w = sum hi*w + sum mid*w + sum lo*w  is three bf16 MMAs whose
 // products are exact and whose fp32 accumulation happens in TMEM -- fp32-grade results (the tolerance class of this
 // path: <= 1e-4 relative, tests/) at tensor-core speed, instead of FFMA loops on the CUDA cores.
 //
@@ -58,7 +58,9 @@ constexpr int F_THREADS = (F_CVT_WARP0 + F_CVT_WARPS) * 32;
 constexpr int F_KC = 16;             // channels per pipeline unit (= one bf16 MMA K step)
 constexpr int F_FSTAGES = 8;         // fp32 halo ring (at most; the host picks the depth that fits)
 constexpr int F_RSTAGES = 6;         // residual / output tile ring (at most)
-constexpr int F_PSTAGES = 3;         // bf16 plane ring
+constexpr int F_PSTAGES = 4;         // bf16 plane ring (at most; 4 or 2)
+constexpr int F_CVT_GROUPS = 2;      // converter groups (alternate units)
+constexpr int F_CVT_GWARPS = F_CVT_WARPS / F_CVT_GROUPS;
 constexpr int F_EPI_BAR = 2;         // named barriers 2, 3: one per epilogue group
 constexpr int F_ACCS = 4;            // TMEM accumulator slots in flight (at most)
 constexpr int F_MAXC = 64;           // channel limit (Cin and Cout)
@@ -67,7 +69,7 @@ constexpr int F_W_BYTES = 9 * F_MAXC * F_MAXC * 2;
 struct F32Params {
   int n, h, w, cin, cout;
   int tiles_w, tiles_h, num_tiles, kchunks;
-  int f_stages, r_stages;            // ring depths chosen by the host
+  int f_stages, r_stages, p_stages;  // ring depths chosen by the host (all even: a slot always belongs to the same group)
   int in_merged;                     // Cin == 16: the halo box is a 3-D box over (W*C, N, H) -- rows of 640 B instead of 64 B
   unsigned long long* dbg;           // QNNB_TRACE builds: CTA 0 timeline (region = role * 1024 words: [count, (tag<<32|idx, ns)...])
   int exp_mode;                      // diagnostics only (QNNB_K4_EXP): 1 = issue one plane's MMAs, 2 = converters skip the split, 3 = epilogue skips math
@@ -138,17 +140,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// x0, x1 -> three bf16x2 words (low half = x0): hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid).
-// Both subtractions are exact in fp32, so hi + mid + lo reproduces x to 24 bits.
+// x0, x1 -> three bf16x2 words (low half = x0).  Each term is the TOP 16 BITS of what is left (truncation, one PRMT per
+// pair): hi = top(x), mid = top(x - hi), lo = top(x - hi - mid).  A bf16 keeps 8 significant bits and every subtraction
+// is exact in fp32, so the three terms peel off 8 + 8 + 8 = all 24 significant bits: hi + mid + lo == x exactly.
+// (Integer byte-permutes and ANDs instead of cvt.rn.bf16x2: the conversion pipe was the converter warps' bottleneck.)
 __device__ __forceinline__ void split3(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-  const float r0 = __fsub_rn(x0, __low2float(h)), r1 = __fsub_rn(x1, __high2float(h));
-  const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
-  const float q0 = __fsub_rn(r0, __low2float(m)), q1 = __fsub_rn(r1, __high2float(m));
-  const __nv_bfloat162 l = __floats2bfloat162_rn(q0, q1);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  mid = *reinterpret_cast<const uint32_t*>(&m);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+  hi = __byte_perm(u0, u1, 0x7632);                                  // {top16(x1), top16(x0)}
+  const float r0 = __fsub_rn(x0, __uint_as_float(u0 & 0xFFFF0000u));
+  const float r1 = __fsub_rn(x1, __uint_as_float(u1 & 0xFFFF0000u));
+  const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+  mid = __byte_perm(v0, v1, 0x7632);
+  const float q0 = __fsub_rn(r0, __uint_as_float(v0 & 0xFFFF0000u));
+  const float q1 = __fsub_rn(r1, __uint_as_float(v1 & 0xFFFF0000u));
+  lo = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);
 }
 
 template <int TH>
@@ -165,13 +170,16 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t bar_base = smem_base + p.off_bar;
   auto ffull = [&](int s) { return bar_base + 8u * s; };
   auto fempty = [&](int s) { return bar_base + 8u * (F_FSTAGES + s); };
-  auto pfull = [&](int b) { return bar_base + 8u * (2 * F_FSTAGES + b); };
-  auto pempty = [&](int b) { return bar_base + 8u * (2 * F_FSTAGES + F_PSTAGES + b); };
-  auto tfull = [&](int a) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + a); };
-  auto tempty = [&](int a) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + F_ACCS + a); };
-  auto rfull = [&](int r) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS + r); };
-  auto rempty = [&](int r) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS + F_RSTAGES + r); };
-  constexpr int NBARS = 2 * F_FSTAGES + 2 * F_PSTAGES + 2 * F_ACCS + 2 * F_RSTAGES;
+  // "planes ready" has one barrier array PER MMA ISSUER (a unit is published to the issuer that will consume it): a
+  // parity wait can only tell adjacent phases apart, so every waiter must see consecutive phases of its barriers; the
+  // two issuers take alternate tiles and would otherwise each see only some of a slot's phases
+  auto pfull = [&](int issuer, int b) { return bar_base + 8u * (2 * F_FSTAGES + issuer * F_PSTAGES + b); };
+  auto pempty = [&](int b) { return bar_base + 8u * (2 * F_FSTAGES + 2 * F_PSTAGES + b); };
+  auto tfull = [&](int a) { return bar_base + 8u * (2 * F_FSTAGES + 3 * F_PSTAGES + a); };
+  auto tempty = [&](int a) { return bar_base + 8u * (2 * F_FSTAGES + 3 * F_PSTAGES + F_ACCS + a); };
+  auto rfull = [&](int r) { return bar_base + 8u * (2 * F_FSTAGES + 3 * F_PSTAGES + 2 * F_ACCS + r); };
+  auto rempty = [&](int r) { return bar_base + 8u * (2 * F_FSTAGES + 3 * F_PSTAGES + 2 * F_ACCS + F_RSTAGES + r); };
+  constexpr int NBARS = 2 * F_FSTAGES + 3 * F_PSTAGES + 2 * F_ACCS + 2 * F_RSTAGES;
   const uint32_t tmem_slot = bar_base + 8u * NBARS;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + p.off_bar + 8 * NBARS);
   const bool has_res = p.epi.res_kind == QNNB_KIND_F32;
@@ -214,9 +222,9 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_y); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < F_FSTAGES; ++s) { mbar_init(ffull(s), 1); mbar_init(fempty(s), F_CVT_WARPS); }
+    for (int s = 0; s < F_FSTAGES; ++s) { mbar_init(ffull(s), 1); mbar_init(fempty(s), F_CVT_GWARPS); }
     for (int r = 0; r < F_RSTAGES; ++r) { mbar_init(rfull(r), 1); mbar_init(rempty(r), 1); }
-    for (int b = 0; b < F_PSTAGES; ++b) { mbar_init(pfull(b), F_CVT_WARPS); mbar_init(pempty(b), 1); }
+    for (int b = 0; b < F_PSTAGES; ++b) { mbar_init(pfull(0, b), F_CVT_GWARPS); mbar_init(pfull(1, b), F_CVT_GWARPS); mbar_init(pempty(b), 1); }
     for (int a = 0; a < F_ACCS; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), F_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -299,25 +307,19 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const uint32_t b_lo0 = (((smem_base + p.off_w) & 0x3FFFFu) >> 4) | ((uint32_t)cout << 16);
       const uint32_t w_tap = (uint32_t)(kchunks * 2 * cout);      // 16-byte units between consecutive taps of the kernel
       const bool np3 = p.np == 3;
-      int b = 0; uint32_t pph = 0;
+      uint32_t uses = 0;                               // four 8-bit counters: own uses of each plane-ring slot
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        if ((it & 1) != my_par) {
-          // the other issuer's tile: still observe every unit's barrier phase -- a parity wait can only tell adjacent
-          // phases apart, so a waiter that skipped a whole ring revolution would alias onto an older phase
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(pfull(b), pph);
-            if (++b == F_PSTAGES) { b = 0; pph ^= 1u; }
-          }
-          continue;
-        }
+        if ((it & 1) != my_par) continue;              // the other issuer's tile
         const int acc = it % p.accs;
         const uint32_t acc_phase = (uint32_t)(it / p.accs) & 1u;
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(pfull(b), pph);
+          const int b = (it * kchunks + kc) % p.p_stages;              // ring slot of this unit
+          mbar_wait(pfull(my_par, b), (uses >> (8 * b)) & 1u);         // parity = how often WE have used this slot
+          uses += 1u << (8 * b);
           ftrace(p, 2, 6, tile);                      // MMA: planes ready
           tc_fence_after();
           const uint32_t a_unit = a_lo0 + (uint32_t)(b * (SL::PSTAGE_BYTES >> 4));
@@ -339,7 +341,6 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             }
           }
           umma_commit(pempty(b));
-          if (++b == F_PSTAGES) { b = 0; pph ^= 1u; }
         }
         umma_commit(tfull(acc));
         ftrace(p, 2, 7, tile);                        // MMA: tile issued
@@ -418,6 +419,7 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<float4*>(rowp + (((ch0 + j) ^ xr) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
+      if (leader) ftrace(p, 3, 13, tile);            // epilogue: math done
       fence_proxy_async();                           // result tile -> visible to the TMA store
       named_bar_sync(F_EPI_BAR + egrp, F_EPI_WARPS * 32);
       if (leader) {
@@ -436,52 +438,60 @@ conv3x3_f32_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     if (leader) tma_store_wait_all();
   } else if (warp >= F_CVT_WARP0) {
     // ===================== converters: fp32 halo -> three bf16 planes =====================
-    const int t = threadIdx.x - F_CVT_WARP0 * 32;
-    int s = 0; uint32_t fph = 0;
-    int b = 0; uint32_t pph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < kchunks; ++kc) {
+    // Two groups of four warps convert alternate units: the per-unit fixed cost (two barrier waits, the proxy fence,
+    // the arrivals) is paid once per 2.8 items per thread instead of 1.4, and two units are in flight.  All ring depths
+    // are even, so a ring slot always belongs to the same group and every group sees consecutive phases of its slots.
+    const int cg = (warp - F_CVT_WARP0) / F_CVT_GWARPS;
+    const int t = threadIdx.x - (F_CVT_WARP0 + cg * F_CVT_GWARPS) * 32;       // 0..127 within the group
+    constexpr int GT = F_CVT_GWARPS * 32;
+    int unit = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int kc = 0; kc < kchunks; ++kc, ++unit) {
+        if ((unit & 1) != cg) continue;
+        const int s = unit % p.f_stages, b = unit % p.p_stages;
+        const uint32_t fph = (uint32_t)(unit / p.f_stages) & 1u, pph = (uint32_t)(unit / p.p_stages) & 1u;
         mbar_wait_parked(ffull(s), fph);
         if (t == 0) ftrace(p, 1, 3, tile);            // converter: halo landed
         mbar_wait_parked(pempty(b), pph ^ 1u);
         if (t == 0) ftrace(p, 1, 4, tile);            // converter: plane slot free
         const uint8_t* fsrc = sg + 0 + s * SL::F_BYTES;
         uint8_t* pdst = sg + p.off_p + b * SL::PSTAGE_BYTES;
-        // every thread owns up to ITEMS (pixel, 8-channel half) items; all their shared-memory loads are issued before the
-        // first conversion so that the (latency-bound) stage overlaps them
-        constexpr int ITEMS = (HALO_PX * 2 + F_CVT_THREADS - 1) / F_CVT_THREADS;
-        float4 va[ITEMS], vc[ITEMS];
+        // (pixel, 8-channel half) items, two per pass: their shared-memory loads are issued before the first conversion
+        constexpr int PASSES = (HALO_PX * 2 + 2 * GT - 1) / (2 * GT);
+#pragma unroll 1
+        for (int ps = 0; ps < PASSES; ++ps) {
+          float4 va[2], vc[2];
 #pragma unroll
-        for (int u = 0; u < ITEMS; ++u) {
-          const int item = t + u * F_CVT_THREADS;
-          if (item < HALO_PX * 2) {
-            const int hp = item >> 1, half = item & 1;
-            va[u] = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32);
-            vc[u] = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32 + 16);
+          for (int u = 0; u < 2; ++u) {
+            const int item = t + (2 * ps + u) * GT;
+            if (item < HALO_PX * 2) {
+              const int hp = item >> 1, half = item & 1;
+              va[u] = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32);
+              vc[u] = *reinterpret_cast<const float4*>(fsrc + hp * 64 + half * 32 + 16);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int item = t + (2 * ps + u) * GT;
+            if (item < HALO_PX * 2 && p.exp_mode != 2) {
+              const int hp = item >> 1, half = item & 1;
+              uint32_t hi[4], mid[4], lo[4];
+              split3(va[u].x, va[u].y, hi[0], mid[0], lo[0]);
+              split3(va[u].z, va[u].w, hi[1], mid[1], lo[1]);
+              split3(vc[u].x, vc[u].y, hi[2], mid[2], lo[2]);
+              split3(vc[u].z, vc[u].w, hi[3], mid[3], lo[3]);
+              uint8_t* d = pdst + half * SL::K8_BYTES + hp * 16;
+              *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(d + SL::PLANE_BYTES) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+              *reinterpret_cast<uint4*>(d + 2 * SL::PLANE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
           }
         }
-#pragma unroll
-        for (int u = 0; u < ITEMS; ++u) {
-          const int item = t + u * F_CVT_THREADS;
-          if (item < HALO_PX * 2 && p.exp_mode != 2) {
-            const int hp = item >> 1, half = item & 1;
-            uint32_t hi[4], mid[4], lo[4];
-            split3(va[u].x, va[u].y, hi[0], mid[0], lo[0]);
-            split3(va[u].z, va[u].w, hi[1], mid[1], lo[1]);
-            split3(vc[u].x, vc[u].y, hi[2], mid[2], lo[2]);
-            split3(vc[u].z, vc[u].w, hi[3], mid[3], lo[3]);
-            uint8_t* d = pdst + half * SL::K8_BYTES + hp * 16;
-            *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(d + SL::PLANE_BYTES) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-            *reinterpret_cast<uint4*>(d + 2 * SL::PLANE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
+        if (t == 0) ftrace(p, 1, 12, tile);           // converter: planes written
         fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) { mbar_arrive(pfull(b)); mbar_arrive(fempty(s)); }
+        if (lane == 0) { mbar_arrive(pfull(it & 1, b)); mbar_arrive(fempty(s)); }
         if (t == 0) ftrace(p, 1, 5, tile);            // converter: planes published
-        if (++s == p.f_stages) { s = 0; fph ^= 1u; }
-        if (++b == F_PSTAGES) { b = 0; pph ^= 1u; }
       }
     }
   }
@@ -501,7 +511,11 @@ int launch_th(const CUtensorMap& mx, const CUtensorMap& mr, const CUtensorMap& m
   // shared-memory plan: bf16 planes (fixed depth), resident kernel, then as many fp32 halo and residual / output stages
   // as fit (both rings need >= 2)
   const int w_bytes = 9 * p.cin * p.cout * 2;
-  const int fixed = F_PSTAGES * SL::PSTAGE_BYTES + w_bytes + 3 * F_MAXC * 4 + 512 + 1024 + 3 * 1024;   // + alignment slack
+  // plane ring: 4 slots (two per converter group) when the minimum fp32 / residual rings still fit, else 2
+  const int other = w_bytes + 3 * F_MAXC * 4 + 512 + 1024 + 3 * 1024;                                     // + alignment slack
+  const int r_one = p.cout == 16 ? 64 * 128 : ceil_div(p.cout, 32) * 128 * 128;
+  p.p_stages = (232448 - other - 4 * SL::PSTAGE_BYTES >= 2 * SL::F_BYTES + 2 * r_one) ? 4 : 2;
+  const int fixed = p.p_stages * SL::PSTAGE_BYTES + other;
   const int budget = 232448 - fixed;
   {
     p.r_bytes = p.cout == 16 ? 64 * 128 : ceil_div(p.cout, 32) * 128 * 128;   // whole swizzled sub-tiles (Cout = 48: the second is half empty)
@@ -511,9 +525,10 @@ int launch_th(const CUtensorMap& mx, const CUtensorMap& mr, const CUtensorMap& m
   if (p.f_stages < 2 || p.f_stages > F_FSTAGES) p.f_stages = 6;
   if (p.r_stages < 2 || p.r_stages > F_RSTAGES) p.r_stages = 6;
   p.r_stages &= ~1;                                // even: a buffer always belongs to the same epilogue group
+  p.f_stages &= ~1;                                // even: a slot always belongs to the same converter group
   while (p.f_stages * SL::F_BYTES + p.r_stages * p.r_bytes > budget) {
     if (p.r_stages > 2 && p.r_stages * p.r_bytes >= p.f_stages * SL::F_BYTES) p.r_stages -= 2;
-    else if (p.f_stages > 2) --p.f_stages;
+    else if (p.f_stages > 2) p.f_stages -= 2;
     else if (p.r_stages > 2) p.r_stages -= 2;
     else { set_error("conv2d: fp32 tensor-core kernel does not fit shared memory (cin=%d cout=%d)", p.cin, p.cout); return QNNB_EINVAL; }
   }
@@ -529,7 +544,7 @@ int launch_th(const CUtensorMap& mx, const CUtensorMap& mr, const CUtensorMap& m
   }
   auto up = [](int v, int a) { return (v + a - 1) / a * a; };
   p.off_p = up(p.f_stages * SL::F_BYTES, 128);
-  p.off_w = up(p.off_p + F_PSTAGES * SL::PSTAGE_BYTES, 128);
+  p.off_w = up(p.off_p + p.p_stages * SL::PSTAGE_BYTES, 128);
   p.off_r = up(p.off_w + w_bytes, 1024);
   p.off_c = p.off_r + p.r_stages * p.r_bytes;
   p.off_bar = up(p.off_c + 3 * F_MAXC * 4, 16);

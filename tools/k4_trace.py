@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 L.check(L.lib().qnnb_debug_set_trace(None, 0))
 b = buf.cpu().numpy()
 names = {1: "TMA   halo load issued", 2: "TMA   residual slot free", 3: "CVT   halo landed", 4: "CVT   plane slot free", 5: "CVT   planes published",
-         6: "MMA   planes ready", 7: "MMA   tile issued", 8: "EPI   residual landed", 9: "EPI   accumulator ready", 10: "EPI   tile stored"}
+         6: "MMA   planes ready", 7: "MMA   tile issued", 8: "EPI   residual landed", 9: "EPI   accumulator ready", 10: "EPI   tile stored", 11: "CVT   loads issued", 12: "CVT   planes written", 13: "EPI   math done"}
 ev = []
 for role in range(4):
     reg = b[role * 1024:(role + 1) * 1024]
