@@ -79,6 +79,7 @@ struct TcParams {
   int tiles_w, tiles_h, tiles_n, m_tiles, num_tiles;
   FastDiv fd_m, fd_w, fd_h;
   int kchunks;            // cin / KC
+  int resident;           // v2: the CTA's nine weight tiles are loaded once and reused by every tile (Cin = 64)
   int out_pitch;          // bytes per staged output row = channels per TMA-store box (<= 128)
   void* y;
   Epi epi;
@@ -534,13 +535,16 @@ struct Smem2 {
   static constexpr bool SPLIT = SPLIT_EPILOGUE && POOL && !OUT_F32;
   static constexpr int NSTG = SPLIT ? 2 : 1;
   static constexpr int BUDGET = 232448 - 1024 - 512 - NSTG * STG_BYTES - HBUFS * HALO_BYTES;
-  static constexpr int ASTAGES = (BUDGET / A_BYTES) > 8 ? 8 : (BUDGET / A_BYTES);
+  // KC = 64: nine stages hold ALL taps of a 64-channel layer, which then stay resident (TcParams::resident)
+  static constexpr int ACAP = (KC == 64) ? 9 : 8;
+  static constexpr int ASTAGES = (BUDGET / A_BYTES) > ACAP ? ACAP : (BUDGET / A_BYTES);
   static constexpr int HALO_OFFSET = 0;
   static constexpr int A_OFFSET = HBUFS * HALO_BYTES;
   static constexpr int STG_OFFSET = A_OFFSET + ASTAGES * A_BYTES;
   static constexpr int BAR_OFFSET = STG_OFFSET + NSTG * STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
   static_assert(ASTAGES >= 3, "not enough shared memory for the weight ring");
+  static_assert(KC != 64 || ASTAGES == 9, "a 64-channel layer must be able to keep its nine weight tiles resident");
 };
 
 template <int KC, int TH, bool POOL, bool OUT_F32, bool SIGN = false>
@@ -620,6 +624,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       int as = 0; uint32_t aphase = 0;
       int issued = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (p.resident && tile != (int)blockIdx.x) break;         // resident weights: one pass fills the nine stages for good
         const int mt = tile - fdiv(tile, p.fd_m) * p.m_tiles;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
@@ -645,6 +650,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
       int as = 0; uint32_t aphase = 0, count = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (p.resident && tile != (int)blockIdx.x) break;
         for (int ks = 0; ks < 9 * p.kchunks; ++ks) {
           mbar_wait(afull(as), aphase);
           st_release_shared(a_ready, ++count);
@@ -685,8 +691,10 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
           for (int tap = 0; tap < 9; ++tap) {
             const int r = tap / 3, s = tap - 3 * r;
 #ifndef QNNB_NO_WATCHER
-            ++a_need;
-            QNNB_CLK(c_afull, { uint32_t spins = 0; while ((int)(a_seen - a_need) < 0) { a_seen = ld_acquire_shared(a_ready); if (++spins > (1u << 26)) __trap(); } });
+            if (!p.resident || it == 0) {
+              ++a_need;
+              QNNB_CLK(c_afull, { uint32_t spins = 0; while ((int)(a_seen - a_need) < 0) { a_seen = ld_acquire_shared(a_ready); if (++spins > (1u << 26)) __trap(); } });
+            }
 #else
             QNNB_CLK(c_afull, mbar_wait(afull(as), aphase));
 #endif
@@ -698,7 +706,7 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #pragma unroll
             for (int k = 0; k < KC / UMMA_K; ++k)
               umma_i8(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            umma_commit(aempty(as));
+            if (!p.resident) umma_commit(aempty(as));
             if (++as == AS) { as = 0; aphase ^= 1u; }
           }
           umma_commit(hempty(hb));                       // halo buffer free once these MMAs retire
@@ -1026,6 +1034,7 @@ int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, vo
   p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
   p.fd_m = make_fastdiv(p.m_tiles); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h);
   p.kchunks = 1;
+  p.resident = 0;
   p.out_pitch = d.cout < TILE_M ? d.cout : TILE_M;
   p.y = y;
   p.epi = make_epi(d.epi);
@@ -1162,6 +1171,9 @@ int launch_conv_tc_v2(const qnnb_conv_desc& d, const void* x, const void* w, voi
   p.y = y;
   p.epi = make_epi(d.epi);
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  // Cin = 64: all nine taps (72 KB) fit the nine-stage weight ring; if every tile of a CTA uses the same channel tile they
+  // are loaded once and stay (no per-tap barrier traffic afterwards)
+  p.resident = (KC == 64 && p.kchunks == 1 && (p.m_tiles == 1 || grid % p.m_tiles == 0) && getenv("QNNB_NO_RESIDENT") == nullptr) ? 1 : 0;
   if (KC == 128) return launch_v2_kc<128>(mw, mx, my, p, grid, g.th, pool, f32, st);
   return launch_v2_kc<64>(mw, mx, my, p, grid, g.th, pool, f32, st);
 }
@@ -1243,6 +1255,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.m_tiles;
   p.fd_m = make_fastdiv(p.m_tiles); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h);
   p.kchunks = d.cin / KC;
+  p.resident = 0;
   p.out_pitch = TILE_M;
   p.y = y;
   p.epi = make_epi(d.epi);
