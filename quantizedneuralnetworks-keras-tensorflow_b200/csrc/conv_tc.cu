@@ -304,6 +304,44 @@ __device__ __forceinline__ void epilogue_role_n(const TcParams& p, const CUtenso
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
         process(vb, 192);
+      } else if constexpr (SPLIT && POOL && TW == 32 && !OUT_F32 && !ILV) {
+        // first-layer geometry (8 rows x 32 px per pixel group), 512-thread kernel: 128 registers per thread rule out
+        // two 64-column buffers, so the accumulator is drained in eight 2 x 16-column pieces -- 16 pixels of image
+        // rows 2pr and 2pr+1, i.e. eight pooled outputs -- double-buffered: the loads of piece k+1 are in flight
+        // while piece k is pooled, scaled and re-quantised
+        constexpr int PC = TW / 2;
+        int va[32], vb[32];
+        auto ld_piece = [&](int k, int (&v)[32]) {
+          const uint32_t a = taddr + (uint32_t)((k >> 1) * 2 * TW + (k & 1) * 16);
+          __syncwarp();
+          tmem_ld16_nowait(a, &v[0]);
+          tmem_ld16_nowait(a + TW, &v[16]);
+        };
+        auto do_piece = [&](int k, int (&v)[32]) {
+          uint8_t* srow = stg + (((grow >> 1) + (k >> 1)) * PC + (k & 1) * 8) * pitch + ch_in_tile;
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc) {
+            const int mx = pick4(v[2 * pc], v[2 * pc + 1], v[16 + 2 * pc], v[16 + 2 * pc + 1]);
+            srow[pc * pitch] = (uint8_t)out_level<SIGN>(qaffine<FOLD>(mx, qc), qm);
+          }
+        };
+        ld_piece(0, va);
+        tmem_ld_wait_dep32(va);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          ld_piece(k + 1, vb);
+          do_piece(k, va);
+          tmem_ld_wait_dep32(vb);
+          if (k + 2 < 8) {
+            ld_piece(k + 2, va);
+          } else {
+            tc_fence_before();                       // all TMEM reads of this tile done: release the accumulator
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+          }
+          do_piece(k + 1, vb);
+          if (k + 2 < 8) tmem_ld_wait_dep32(va);
+        }
       } else if constexpr (SPLIT) {
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {

@@ -169,6 +169,28 @@ __device__ __forceinline__ void tmem_ld_wait_dep(int (&v)[64]) {
       : "memory");
 }
 
+// 32 lanes x 16 consecutive columns, no wait (pair with tmem_ld_wait_dep32)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, int* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld that "redefines" 32 destination registers of earlier loads (see tmem_ld_wait_dep)
+__device__ __forceinline__ void tmem_ld_wait_dep32(int (&v)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+        "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+        "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+        "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
+}
+
 // UMMA shared-memory matrix descriptor, K-major operand whose rows are KC bytes wide and stored with the
 // KC-byte swizzle (KC = 64 or 128): 8-row groups are 8*KC bytes apart (SBO); LBO is unused for swizzled
 // K-major layouts (set to 16 B); version = 1 (Blackwell); layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
