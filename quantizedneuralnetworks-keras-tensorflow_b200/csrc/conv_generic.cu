@@ -64,7 +64,7 @@ conv_generic_kernel(const ConvP p) {
   constexpr int TPX = T::TPX, TPY = T::TPY;
   if (threadIdx.x == 0) griddep_launch_dependents();
   griddep_wait();
-  __shared__ uint32_t sa[T::MAX_IY * T::MAX_IX * CKW];
+  __shared__ __align__(16) uint32_t sa[T::MAX_IY * T::MAX_IX * CKW];
   __shared__ __align__(16) uint32_t sw[MAXK * MAXK * CKW * TC];
 
   const int tid = threadIdx.x;
@@ -111,6 +111,32 @@ conv_generic_kernel(const ConvP p) {
     const int kc = min(CKW, p.kwords - k0);
     __syncthreads();
     // ---- stage the input halo: sa[(iy*IW + ix)*CKW + k]
+    // Fast path (full chunk, 16-byte aligned rows): one item = one halo pixel = its 8 K words as two 128-bit loads
+    // (independent, two items in flight per thread) instead of eight scalar loads with per-word index arithmetic.
+    bool a_vec;
+    if constexpr (KIND == QNNB_KIND_F32) a_vec = (kc == CKW) && (p.cin & 3) == 0;
+    else if constexpr (KIND == QNNB_KIND_B1) a_vec = (kc == CKW) && (p.kwords & 3) == 0;
+    else a_vec = (kc == CKW) && (p.cin & 15) == 0;
+    if (a_vec) {
+      const int npix = IH * IW;
+#pragma unroll 2
+      for (int pix = tid; pix < npix; pix += 256) {
+        const int iy = pix / IW, ix = pix - iy * IW;
+        const int gy = iy0 + iy, gx = ix0 + ix;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+          const long long pixel = ((long long)img * p.h + gy) * p.w + gx;
+          const uint4* src;
+          if constexpr (KIND == QNNB_KIND_F32) src = reinterpret_cast<const uint4*>((const float*)p.x + pixel * p.cin + k0);
+          else if constexpr (KIND == QNNB_KIND_B1) src = reinterpret_cast<const uint4*>((const uint32_t*)p.x + pixel * p.kwords + k0);
+          else src = reinterpret_cast<const uint4*>((const uint8_t*)p.x + pixel * p.cin + k0 * 4);
+          v0 = __ldg(src);
+          v1 = __ldg(src + 1);
+        }
+        *reinterpret_cast<uint4*>(&sa[pix * CKW]) = v0;
+        *reinterpret_cast<uint4*>(&sa[pix * CKW + 4]) = v1;
+      }
+    } else
     for (int i = tid; i < IH * IW * CKW; i += 256) {
       int k = i % CKW;
       int pix = i / CKW;
@@ -138,6 +164,34 @@ conv_generic_kernel(const ConvP p) {
       sa[i] = v;
     }
     // ---- stage the weights: sw[(tap*CKW + k)*TC + c]
+    // Fast path: one item = (tap, channel) = 8 consecutive K words of the packed kernel as vector loads
+    bool w_vec;
+    if constexpr (KIND == QNNB_KIND_F32) w_vec = (kc == CKW) && (p.cin_pad & 7) == 0;
+    else w_vec = (kc == CKW) && (p.kwords & 3) == 0;
+    if (w_vec) {
+#pragma unroll 2
+      for (int item = tid; item < taps * TC; item += 256) {
+        const int c = item % TC, t = item / TC;
+        const int co = c_base + c;
+        uint32_t wd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (co < p.cout) {
+          if constexpr (KIND == QNNB_KIND_F32) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>((const int8_t*)p.wts + ((long long)co * taps + t) * p.cin_pad + k0));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t word = k < 4 ? raw.x : raw.y;
+              wd[k] = __float_as_uint((float)(int)(int8_t)(word >> (8 * (k & 3))));
+            }
+          } else {
+            const uint4* src = reinterpret_cast<const uint4*>((const uint32_t*)p.wts + ((long long)co * taps + t) * p.kwords + k0);
+            const uint4 a = __ldg(src), b = __ldg(src + 1);
+            wd[0] = a.x; wd[1] = a.y; wd[2] = a.z; wd[3] = a.w; wd[4] = b.x; wd[5] = b.y; wd[6] = b.z; wd[7] = b.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sw[(t * CKW + k) * TC + c] = wd[k];
+      }
+    } else
     for (int i = tid; i < taps * CKW * TC; i += 256) {
       int k = i % CKW;
       int r = i / CKW;
