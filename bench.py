@@ -73,30 +73,6 @@ def int8_peak_tops(pk):
 
 
 # ------------------------------------------------------------------------------ algorithmic work
-def layer_work(cf, batch):
-    """Per fused step: (name, ops, bytes) with ops = 2*MACs (no padding) and bytes = input + output at
-    deployed width + packed weights."""
-    out = []
-    h = cf.dim
-    cin = cf.channels
-    in_bytes_per = 1
-    blocks = [(max(cf.nla, 1), cf.nfa), (cf.nlb, cf.nfb), (cf.nlc, cf.nfc)]
-    li = 0
-    for nl, nf in blocks:
-        for j in range(nl):
-            pooled = (j == nl - 1)
-            macs = batch * h * h * 9 * cin * nf
-            oh = h // 2 if pooled else h
-            byts = batch * h * h * cin * in_bytes_per + batch * oh * oh * nf + 9 * cin * nf
-            out.append(("conv%d" % li, 2 * macs, byts))
-            li += 1
-            cin = nf
-            h = oh
-    feat = h * h * cin
-    out.append(("dense", 2 * batch * feat * cf.classes, batch * feat + batch * cf.classes * 4 + feat * cf.classes))
-    return out
-
-
 KIND_BYTES = {"u8": 1.0, "i8": 1.0, "b1": 1.0 / 8.0, "f32": 4.0}
 
 

@@ -21,10 +21,13 @@
 // 4-D TMA store of the whole tile ({128, TW', TH', TN} box of the NHWC output; out-of-range images are
 // clipped by the TMA unit), so HBM sees full 128-byte rows.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..11 = epilogue (two warps per TMEM lane quarter, each takes half of the columns).
-// Pipelines: smem ring full/empty (TMA <-> MMA), 2 TMEM accumulators full/empty (MMA <-> epilogue),
-// persistent static tile schedule.
+// Warp roles (384 threads; every single-threaded role runs under elect.sync): warp 0 = TMA producer (v2: halo tiles),
+// warp 1 = MMA issuer, warp 2 = TMEM allocator (v2: weight-stage watcher), warp 3 = (v2) weight-tile TMA producer,
+// warps 4..11 = epilogue: lock-step (two warps per TMEM lane quarter, each half of the columns) or, where a second
+// staging tile fits, two independent groups of four warps draining alternate tiles.
+// Pipelines: smem rings full/empty (TMA <-> MMA), 2 TMEM accumulators full/empty (MMA <-> epilogue), persistent static
+// tile schedule (tile index decoded by multiply-shift).  Layers chain through programmatic dependent launch: the next
+// kernel's prologue and weight loads run while this one drains (griddepcontrol, common.cuh).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 

@@ -104,3 +104,64 @@ def test_no_cpu_fallback():
         m.predict(np.zeros((1, 32, 32, 3), np.uint8))
     with pytest.raises(ValueError):
         L.ptr(torch.zeros(4))
+
+
+def _desc(n, h, w, cin, cout, k=3, stride=1, in_kind=None, act=None, abits=4, pool=0, scale=1.0 / 64, res_kind=None):
+    d = L.ConvDesc()
+    d.n, d.h, d.w, d.cin, d.cout, d.kh, d.kw, d.stride = n, h, w, cin, cout, k, k, stride
+    d.in_kind = L.KIND_I8 if in_kind is None else in_kind
+    d.impl = L.IMPL_AUTO
+    d.epi.acc_scale = scale
+    d.epi.res_kind = L.KIND_NONE if res_kind is None else res_kind
+    d.epi.residual = 0x1000 if res_kind is not None else None       # any non-null value: the query never dereferences it
+    d.epi.act = L.ACT_QUANT if act is None else act
+    d.epi.abits = abits
+    d.epi.pool = pool
+    d.epi.res_mul = 1.0
+    return d
+
+
+def test_kernel_selection_query_is_pure_host_logic():
+    """qnnb_conv2d_tc_supported (which the plan uses to pick the storage form of +-1 maps) needs no GPU: check the
+    shapes of BASELINE.json's configs land on the kernels DESIGN.md says they do."""
+    h = L.lib()
+    q = lambda d: h.qnnb_conv2d_tc_supported(C.byref(d))
+    # cfg3 / cfg4 interior layers: int8 implicit GEMM on tcgen05 (K1)
+    assert q(_desc(1024, 16, 16, 64, 128, pool=2)) == 1
+    assert q(_desc(1024, 8, 8, 128, 256, pool=2)) == 1
+    assert q(_desc(4096, 32, 32, 256, 256, abits=8, scale=1.0 / (128 * 128))) == 1
+    # first layer: uint8 RGB, 32 wide (K5); and its +-1 (full-bnn) form with int8 levels out
+    assert q(_desc(1024, 32, 32, 3, 64, in_kind=L.KIND_U8, pool=2, scale=1.0 / (255 * 8))) == 1
+    assert q(_desc(256, 32, 32, 3, 64, in_kind=L.KIND_U8, act=L.ACT_SIGN_I8, pool=2, scale=1.0 / 255)) == 1
+    assert q(_desc(256, 16, 16, 64, 128, act=L.ACT_SIGN_I8, pool=2, scale=1.0)) == 1
+    # bit-packed +-1 output, MNIST maps, narrow layers, strides, residuals, non-power-of-two scales: generic kernel
+    assert q(_desc(256, 16, 16, 64, 128, act=L.ACT_SIGN, pool=2, scale=1.0)) == 0
+    assert q(_desc(100, 14, 14, 64, 64, abits=2, pool=2)) == 0
+    assert q(_desc(100, 28, 28, 1, 64, in_kind=L.KIND_U8, abits=2, pool=2)) == 0
+    assert q(_desc(1024, 32, 32, 16, 16)) == 0
+    assert q(_desc(1024, 32, 32, 64, 128, stride=2)) == 0
+    assert q(_desc(1024, 16, 16, 64, 128, res_kind=L.KIND_I8)) == 0
+    assert q(_desc(1024, 16, 16, 64, 128, scale=0.3)) == 0
+    # fp32 activations (qnn / bnn / tnn nets): bf16-split tensor-core kernel (K4) for 16..64 channels, 3x3 stride 1
+    f32 = dict(in_kind=L.KIND_F32, act=L.ACT_LEAKY)
+    assert q(_desc(1024, 32, 32, 16, 16, **f32)) == 1
+    assert q(_desc(1024, 16, 16, 32, 32, res_kind=L.KIND_F32, **f32)) == 1
+    assert q(_desc(1024, 8, 8, 64, 64, in_kind=L.KIND_F32, act=L.ACT_NONE)) == 1
+    assert q(_desc(1024, 32, 32, 16, 32, stride=2, **f32)) == 0
+    assert q(_desc(1024, 32, 32, 3, 16, **f32)) == 0
+    assert q(_desc(1024, 16, 16, 128, 128, **f32)) == 0
+    assert q(_desc(1024, 16, 16, 32, 32, pool=2, **f32)) == 0
+    # malformed descriptors are "not supported", never a crash
+    assert q(_desc(1024, 16, 16, 64, 128, k=5)) == 0
+    assert h.qnnb_conv2d_tc_supported(None) == 0
+
+
+def test_dense_rejects_pooled_integer_input_without_a_gpu():
+    h = L.lib()
+    d = L.DenseDesc()
+    d.n, d.fin, d.units, d.in_kind, d.softmax = 4, 64, 10, L.KIND_I8, 0
+    d.epi.acc_scale = 1.0
+    d.epi.res_kind = L.KIND_NONE
+    d.avg_positions = 64
+    rc = h.qnnb_dense(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), C.c_void_p(0x1000), None, None)
+    assert rc == L.EINVAL and b"avg_positions" in h.qnnb_last_error()
