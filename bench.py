@@ -119,7 +119,10 @@ def ncu_traffic(workload, step_indices, n_steps):
         return None
     rows = list(csv.reader(open(path)))
     hdr, body = rows[0], rows[1:]
-    if len(body) != n_steps:
+    if len(body) > n_steps:
+        return None
+    step_indices = [k for k in step_indices if k < len(body)]      # a partial capture covers the first kernels of a forward
+    if not step_indices:
         return None
     def col(prefix):
         for i, h in enumerate(hdr):
