@@ -142,7 +142,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // x0, x1 -> three bf16x2 words (low half = x0).  Each term is the TOP 16 BITS of what is left (truncation, one PRMT per
 // pair): hi = top(x), mid = top(x - hi), lo = top(x - hi - mid).  A bf16 keeps 8 significant bits and every subtraction
-// is exact in fp32, so the three terms peel off 8 + 8 + 8 = all 24 significant bits: hi + mid + lo == x exactly.
+// is exact in fp32, so the three terms peel off 8 + 8 + 8 = all 24 significant bits: hi + mid + lo == x exactly
+// (for |x| >= 2^-100; below that the residuals become subnormal and the absolute error is < 2^-126 --
+// tests/test_kernel_arithmetic_cpu.py).
 // (Integer byte-permutes and ANDs instead of cvt.rn.bf16x2: the conversion pipe was the converter warps' bottleneck.)
 __device__ __forceinline__ void split3(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
   const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
