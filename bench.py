@@ -494,7 +494,9 @@ def run_ours(args):
                    "sample": "%d images, median of 3 (oracle O2a: torch-CPU fp32 restatement of the reference graph)" % sample}
         line = {"metric": metric_name(args.workload), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8 (int32 accumulate, fp32 epilogue)", "data": "synthetic",
+                "dtype": ("int8 (int32 accumulate, fp32 epilogue)" if cf.network_type in ("full-qnn", "full-bnn", "qbnn", "qtnn")
+                          else "fp32 activations as an exact 3 x bf16 split x integer kernel levels (fp32 accumulate)"),
+                "data": "synthetic",
                 "config": {"workload": ("%s: %s VGG %s w%da%d %d/%d/%d x %d/%d/%d, batch %d per GPU" % (
                                args.workload, cf.dataset, cf.network_type, cf.wbits, cf.abits, cf.nla, cf.nlb, cf.nlc, cf.nfa, cf.nfb, cf.nfc, batch))
                            if cf.architecture == "VGG" else ("%s: %s ResNet-%d %s w%da%d, batch %d per GPU" % (
