@@ -240,3 +240,26 @@ def test_evaluate_matches_host_metrics():
     assert abs(acc - float((p.argmax(1) == labels).mean())) < 1e-9
     want_loss = float(np.mean(-np.log(np.clip(p[np.arange(64), labels], 1e-7, 1))))
     assert abs(loss - want_loss) <= 1e-4 * max(want_loss, 1.0)
+
+
+# --------------------------------------------------------------------------- BASELINE.json full batch sizes: size-independent properties
+@pytest.mark.parametrize("name,n,chunk", [("cfg3", 1024, 256), ("cfg2", 256, 64), ("cfg4", 4096, 1024), ("cfg5", 1024, 256)])
+def test_full_size_batches_properties(name, n, chunk):
+    """At the batch sizes BASELINE.json quotes, where the oracle cannot run the whole batch in seconds:
+    (a) images are independent -- one forward over the full batch equals the same batch run in chunks, bit for bit;
+    (b) permuting the batch permutes the logits; (c) a sample of images spread over the batch equals the exact oracle
+    (bit-exact for the integer nets, north_star tolerance for the fp32-activation net)."""
+    cf, model, nodes = build(CONFIGS[name], bn="spread")
+    x = images(cf, n, seed=4321)
+    full = model.predict(x)
+    assert full.shape == (n, 10) and np.isfinite(full).all()
+    assert np.array_equal(model.predict(x, batch_size=chunk), full)
+    perm = np.random.default_rng(1).permutation(n)
+    assert np.array_equal(model.predict(x[perm]), full[perm])
+    idx = np.linspace(0, n - 1, 8).astype(int)
+    want = exact.forward(nodes, x[idx])
+    if cf.network_type in ("full-qnn", "full-bnn"):
+        assert np.array_equal(full[idx], want)
+    else:
+        assert rel_err(full[idx], want) <= 1e-4
+        assert np.array_equal(full[idx].argmax(1), want.argmax(1))
