@@ -16,6 +16,13 @@ import numpy as np
 F32 = np.float32
 _NAME_COUNTS: dict = {}
 _RNG = np.random.default_rng(0)
+_WEIGHTS_EPOCH = 0
+
+
+def weights_epoch() -> int:
+    """Process-wide counter bumped by every ``layer.set_weights``; plans use it as an O(1) staleness test before
+    comparing per-layer versions (plan.Plan._sync_weights)."""
+    return _WEIGHTS_EPOCH
 
 
 def set_seed(seed: int):
@@ -79,7 +86,13 @@ class Layer:
             self._input_shape_arg = (None,) + tuple(input_shape)
         self.input_shape = None
         self.output_shape = None
-        self._plan_cache = None
+        self._wversion = 0
+
+    def _touch(self):
+        """Weights changed: any plan that cached device copies derived from them must rebuild (plan.py)."""
+        global _WEIGHTS_EPOCH
+        self._wversion += 1
+        _WEIGHTS_EPOCH += 1
 
     # ---- Keras protocol
     def build(self, input_shape):
@@ -180,7 +193,7 @@ class BatchNormalization(Layer):
             if a.shape != self.gamma.shape:
                 raise ValueError("BatchNormalization %s: bad weight shape %s" % (self.name, a.shape))
         self.gamma, self.beta, self.moving_mean, self.moving_variance = arrs
-        self._plan_cache = None
+        self._touch()
 
     def constants(self):
         from .kernels import bn_constants
@@ -354,6 +367,10 @@ class _ModelBase:
 
     # to be provided by subclasses: self.layers (ordered), self._nodes() -> [(layer, [input node ids])]
     def _invalidate(self):
+        """Drop the fused plans (graph structure or weights changed); their captured graphs, static buffers and
+        cached constants are released right here, not whenever the garbage collector gets to them."""
+        for pl in self._plans.values():
+            pl.close()
         self._plans = {}
 
     def get_layer(self, name=None, index=None):

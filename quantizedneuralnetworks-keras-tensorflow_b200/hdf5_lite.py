@@ -173,8 +173,41 @@ class H5File:
             yield from self.walk(addr, prefix + "/" + name)
 
 
-def read_keras_weights(path):
-    """-> {layer name: {weight name: array}} from a Keras checkpoint (weight name without the ':0' suffix)."""
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _attributes(f, header_addr):
+    """{name: value} of the version-1 attribute messages of an object: fixed-length string arrays (Keras'
+    ``layer_names`` / ``weight_names``) come back as lists of str, numeric ones as arrays; others are skipped."""
+    out = {}
+    for mtype, _, body, size in f.messages(header_addr):
+        if mtype != 0x0C or f.d[body] != 1:
+            continue
+        nsz, tsz, ssz = f._u16(body + 2), f._u16(body + 4), f._u16(body + 6)
+        off = body + 8
+        name = f.d[off:off + nsz].split(b"\x00")[0].decode("utf-8")
+        off += _pad8(nsz)
+        cls, esize = f.d[off] & 0x0F, f._u32(off + 4)
+        bits0 = f.d[off + 1]
+        off += _pad8(tsz)
+        sver, rank = f.d[off], f.d[off + 1]
+        dims = tuple(f._u64(off + (8 if sver == 1 else 4) + 8 * i) for i in range(rank))
+        off += _pad8(ssz)
+        count = int(np.prod(dims)) if dims else 1
+        if cls == 3:                                      # fixed-length strings
+            out[name] = [f.d[off + i * esize:off + (i + 1) * esize].split(b"\x00")[0].decode("utf-8") for i in range(count)]
+        elif cls in (0, 1) and not (bits0 & 1):
+            dt = ({2: np.float16, 4: np.float32, 8: np.float64}[esize] if cls == 1
+                  else np.dtype("%s%d" % ("i" if bits0 & 0x08 else "u", esize)))
+            out[name] = np.frombuffer(f.d, dtype=dt, count=count, offset=off).reshape(dims).copy()
+    return out
+
+
+def read_keras_weights(path, with_order=False):
+    """-> {layer name: {weight name: array}} from a Keras checkpoint (weight name without the ':0' suffix).
+    ``with_order``: also return {layer name: [weight names in the file's ``weight_names`` order]} (only for layers
+    whose group carries that attribute) and the file's ``layer_names`` list (or None)."""
     f = H5File(path)
     out = {}
     for p, arr in f.walk():
@@ -187,29 +220,89 @@ def read_keras_weights(path):
             continue
         layer, wname = parts[0], parts[-1].split(":")[0]
         out.setdefault(layer, {})[wname] = arr
-    return out
+    if not with_order:
+        return out
+    root = f.root_header
+    kids = f.children(root)
+    if "model_weights" in kids:
+        root = kids["model_weights"]
+        kids = f.children(root)
+    layer_names = _attributes(f, root).get("layer_names")
+    if not isinstance(layer_names, list):
+        layer_names = None
+    worder = {}
+    for lname, addr in kids.items():
+        wn = _attributes(f, addr).get("weight_names")
+        if isinstance(wn, list) and wn:
+            worder[lname] = [w.split("/")[-1].split(":")[0] for w in wn]
+    return out, worder, layer_names
 
 
 _ORDER = {"kernel": 0, "bias": 1, "gamma": 0, "beta": 1, "moving_mean": 2, "moving_variance": 3}
 
 
-def load_keras_weights(model, path):
-    tensors = read_keras_weights(path)
-    for layer in model.layers:
-        want = layer.weight_names()
-        if not want:
-            continue
-        grp = tensors.get(layer.name)
-        if grp is None:
-            # the reference's QuantizedDense calls Layer.__init__ twice, so its auto-name is e.g. quantized_dense_2
-            base = layer.name.rsplit("_", 1)[0]
-            cands = [k for k in tensors if k.rsplit("_", 1)[0] == base and sorted(tensors[k]) == sorted(want)]
-            mine = [l for l in model.layers if l.name.rsplit("_", 1)[0] == base]
-            if len(cands) == len(mine):
-                cands.sort(key=lambda k: int(k.rsplit("_", 1)[1]))
-                mine.sort(key=lambda l: int(l.name.rsplit("_", 1)[1]))
-                grp = tensors[cands[mine.index(layer)]]
-        if grp is None:
+def _split_auto_name(name):
+    """'quantized_conv2d_12' -> ('quantized_conv2d', 12); names without a numeric suffix -> (name, None)."""
+    base, _, suf = name.rpartition("_")
+    return (base, int(suf)) if base and suf.isdigit() else (name, None)
+
+
+def load_keras_weights(model, path, by_name=False):
+    """``model.load_weights(path)`` (test_resnet.py:66, train.py:113-115).
+
+    Keras assigns a checkpoint's weighted layers to the model's weighted layers IN ORDER and ignores their names
+    (``by_name=False``).  Auto-generated names (``<class>_<k>``, k from a per-class process-wide counter) therefore
+    carry no absolute meaning: the checkpoint may come from a session that had built other models first, and so may
+    this model.  What both sides do agree on is the creation order of the layers of one class -- it is the order of
+    the builder's code (models/vgg.py, models/resnet.py) -- so the k-th checkpoint layer of a class is bound to the
+    k-th model layer of that class, whatever their counters say (this also absorbs the reference's QuantizedDense
+    naming quirk, whose double ``__init__`` makes the first one ``quantized_dense_2``).  Layers with explicit names
+    match by name.  Counts per class and every tensor shape are validated; ``by_name=True`` matches names only."""
+    tensors, worder, layer_names = read_keras_weights(path, with_order=True)
+    file_layers = [n for n in (layer_names or sorted(tensors)) if n in tensors and tensors[n]]
+    for n in tensors:                                     # groups the attribute does not list (never in Keras files)
+        if n not in file_layers and tensors[n]:
+            file_layers.append(n)
+    mine = [l for l in model.layers if l.weight_names()]
+    binding = {}
+    if by_name:
+        for l in mine:
+            if l.name in tensors:
+                binding[l.name] = l.name
+    else:
+        fgroups, mgroups = {}, {}
+        for n in file_layers:
+            fgroups.setdefault(_split_auto_name(n)[0] if _split_auto_name(n)[1] is not None else ("=" + n), []).append(n)
+        for l in mine:
+            mgroups.setdefault(_split_auto_name(l.name)[0] if _split_auto_name(l.name)[1] is not None else ("=" + l.name), []).append(l.name)
+        for base, names in mgroups.items():
+            have = fgroups.get(base, [])
+            if len(have) != len(names):
+                raise ValueError("checkpoint %s holds %d weighted %r layers, the model has %d"
+                                 % (path, len(have), base.lstrip("="), len(names)))
+            if base.startswith("="):
+                binding[names[0]] = have[0]
+            else:
+                have = sorted(have, key=lambda n: _split_auto_name(n)[1])
+                for mn, fn in zip(sorted(names, key=lambda n: _split_auto_name(n)[1]), have):
+                    binding[mn] = fn
+        extra = set(fgroups) - set(mgroups)
+        if extra:
+            raise ValueError("checkpoint %s holds weighted layers the model lacks: %s" % (path, sorted(b.lstrip("=") for b in extra)))
+    for layer in mine:
+        src = binding.get(layer.name)
+        if src is None:
+            if by_name:
+                continue
             raise ValueError("checkpoint %s has no weights for layer %s" % (path, layer.name))
-        layer.set_weights([np.asarray(grp[n], np.float32) for n in sorted(want, key=lambda n: _ORDER[n])])
+        grp, want = tensors[src], layer.weight_names()
+        if sorted(grp) != sorted(want):
+            raise ValueError("checkpoint layer %s holds %s, layer %s expects %s" % (src, sorted(grp), layer.name, sorted(want)))
+        order = worder.get(src)
+        if not order or sorted(order) != sorted(want):
+            order = sorted(want, key=lambda n: _ORDER[n])
+        if order != want:
+            # the file lists the tensors in another order than this layer's set_weights takes them: go by name
+            order = want
+        layer.set_weights([np.asarray(grp[n], np.float32) for n in order])      # validates every shape
     return model

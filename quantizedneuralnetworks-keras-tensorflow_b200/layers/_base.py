@@ -125,6 +125,7 @@ class QLinearBase(Layer):
                 raise ValueError("%s: bias shape %s != %s" % (self.name, b.shape, self.bias.shape))
             self.bias = np.ascontiguousarray(b)
         self._packed = {}
+        self._touch()
 
     # -- device-side caches
     def packed_kernel(self, device, wfmt, kernel_override=None, tag=""):

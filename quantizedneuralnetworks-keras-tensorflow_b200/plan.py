@@ -9,6 +9,9 @@ kernel over the un-pooled map with the packed kernel replicated per pixel.
 """
 from __future__ import annotations
 
+import gc
+import weakref
+
 import numpy as np
 import torch
 
@@ -35,23 +38,38 @@ def _act_of(layer):
 
 
 class _Handle:
-    """Result of Plan.predict_async: ``result()`` waits for the slot's D2H copy and returns a private copy."""
+    """Result of Plan.predict_async: ``result()`` waits for the slot's D2H copy and returns a private copy.
+
+    A slot is owned by at most one unread handle.  When the ring wraps around onto a slot whose handle has not been
+    read yet, the plan first completes that handle (``_settle``: wait + private copy), so a late ``result()`` still
+    returns ITS batch; ``gen`` guards against a stale handle touching a slot that has since been reused."""
 
     def __init__(self, slot):
         self._slot = slot
+        self._gen = slot["gen"]
         self._out = None
 
+    def _settle(self):
+        slot = self._slot
+        if self._out is None and slot is not None:
+            if slot["gen"] != self._gen:
+                raise RuntimeError("predict_async: the slot of this handle was recycled before its result was kept")
+            slot["event"].synchronize()
+            self._out = slot["host"].clone()
+            slot["owner"] = None
+            self._slot = None
+
     def result(self):
-        if self._out is None:
-            self._slot["event"].synchronize()
-            self._out = self._slot["host"].clone()
-            self._slot["busy"] = False
+        self._settle()
         return self._out
 
 
 class Plan:
     def __init__(self, model, impl=L.IMPL_AUTO):
-        self.model = model
+        # weak: the model owns its plans (model._plans); a strong back-reference would make every dead model -- with
+        # the CUDA graphs and pool memory of its plans -- wait for the cyclic collector, which may then run in the
+        # middle of somebody else's stream capture
+        self._model_ref = weakref.ref(model)
         self.impl = int(impl)
         ins, outs = model._graph()
         self.order = E.topo_order(outs)
@@ -64,6 +82,44 @@ class Plan:
         self._slots = {}
         self._compile()
         self.launches_per_forward = len(self.steps)
+        self._layers = [t.layer for t in self.order]
+        self._epoch = -1
+        self._versions = None
+        self._sync_weights()
+
+    @property
+    def model(self):
+        return self._model_ref()
+
+    # ------------------------------------------------------------------ lifetime / staleness
+    def close(self):
+        """Drop everything that lives on the device on behalf of this plan: captured graphs with their private
+        pools, static input / output buffers, pinned result buffers, cached per-step constants."""
+        for ring in self._slots.values():
+            for slot in ring["slots"]:
+                owner = slot.get("owner")
+                if owner is not None:
+                    try:
+                        owner._settle()                 # an outstanding handle keeps its result
+                    except Exception:
+                        pass
+                slot.clear()
+        self._slots = {}
+        for st in self.steps:
+            st.dev = {}
+
+    def _sync_weights(self):
+        """Layers bump a version on every ``set_weights`` (engine.Layer._touch).  If any layer of this plan changed
+        since the last launch, the cached BN constants and every captured graph (they hold raw pointers to the old
+        packed kernels / biases) are dropped and rebuilt lazily -- ``model.layers[i].set_weights(...)`` after a first
+        ``predict`` must never replay stale buffers."""
+        if self._epoch == E.weights_epoch():
+            return
+        versions = [getattr(l, "_wversion", 0) for l in self._layers]
+        if self._versions is not None and versions != self._versions:
+            self.close()
+        self._versions = versions
+        self._epoch = E.weights_epoch()
 
     # ------------------------------------------------------------------ compile
     def _consumers(self):
@@ -288,6 +344,7 @@ class Plan:
 
     def run(self, x) -> dict:
         """One forward over a device batch.  Returns the environment (tensor index -> QTensor)."""
+        self._sync_weights()
         env = {self.input_idx: K.as_qtensor(x)}
         for st in self.steps:
             self.run_step(st, env)
@@ -307,6 +364,39 @@ class Plan:
     # copy are enqueued back to back on the slot's stream, so consecutive batches overlap copy and compute.
     PIPELINE_DEPTH = 3
 
+    def _capture(self, x_dev, st):
+        """Capture one forward over the static input ``x_dev`` on stream ``st``.  Returns (graph | None, output).
+
+        Object finalisers must not run while the stream is capturing: destroying an old ``torch.cuda.CUDAGraph``
+        (or freeing its pool) issues CUDA calls that are illegal under a global-mode capture and invalidate it.
+        So: collect garbage BEFORE the capture, keep the cyclic collector off during it, and capture in thread-local
+        mode (other threads' CUDA calls do not touch this capture either).  If the capture still fails the slot runs
+        the same launches eagerly -- slower on the host, identical results."""
+        gc.collect()
+        torch.cuda.synchronize()
+        st.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
+                    out_dev = self.forward(x_dev)
+            return g, out_dev
+        except Exception:
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            del g
+            with torch.cuda.stream(st):
+                out_dev = self.forward(x_dev)
+            st.synchronize()
+            return None, out_dev
+        finally:
+            if gc_was_on:
+                gc.enable()
+
     def _slot(self, shape, dtype):
         key = (tuple(shape), dtype)
         ring = self._slots.setdefault(key, {"slots": [], "next": 0})
@@ -317,38 +407,41 @@ class Plan:
             if not ring["slots"]:
                 self.forward(x_dev)                     # packs weights / uploads constants outside the capture
                 torch.cuda.synchronize()
-            st.wait_stream(torch.cuda.current_stream())
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(st):
-                with torch.cuda.graph(g, stream=st):
-                    out_dev = self.forward(x_dev)
+            g, out_dev = self._capture(x_dev, st)
             out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype).pin_memory()
             ring["slots"].append({"stream": st, "x": x_dev, "graph": g, "out": out_dev, "host": out_host,
-                                  "event": torch.cuda.Event(), "busy": False})
+                                  "event": torch.cuda.Event(), "owner": None, "gen": 0})
         slot = ring["slots"][ring["next"] % len(ring["slots"])] if len(ring["slots"]) == self.PIPELINE_DEPTH else ring["slots"][-1]
         ring["next"] += 1
         return slot
 
     def predict_async(self, x):
         """Enqueue one host batch (numpy array or CPU tensor, ideally pinned) and return a handle whose
-        ``result()`` blocks until the logits are back in host memory.  At most PIPELINE_DEPTH handles may be
-        outstanding: a slot is recycled (after waiting for it) when the ring wraps around."""
+        ``result()`` blocks until the logits are back in host memory.  PIPELINE_DEPTH batches are in flight at most:
+        when the ring wraps around onto a slot whose handle has not been read, that handle is completed first (its
+        result is copied out), so handles may be read late and in any order."""
         if not torch.cuda.is_available():
             raise RuntimeError("predict needs a CUDA device: this package has no CPU path")
         src = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x.contiguous()
         if src.is_cuda:
             raise ValueError("predict_async takes host batches; use predict() for device tensors")
+        self._sync_weights()
         slot = self._slot(src.shape, src.dtype)
-        if slot["busy"]:
-            slot["event"].synchronize()
-        slot["busy"] = True
+        if slot["owner"] is not None:
+            slot["owner"]._settle()
+        slot["gen"] += 1
         with torch.cuda.stream(slot["stream"]):
             slot["x"].copy_(src, non_blocking=True)
-            slot["graph"].replay()
+            if slot["graph"] is not None:
+                slot["graph"].replay()
+            else:
+                slot["out"].copy_(self.forward(slot["x"]))
             slot["host"].copy_(slot["out"], non_blocking=True)
             slot["event"].record(slot["stream"])
         self.launches += self.launches_per_forward
-        return _Handle(slot)
+        h = _Handle(slot)
+        slot["owner"] = h
+        return h
 
     def predict(self, x, batch_size=None, return_logits=False):
         as_numpy = isinstance(x, np.ndarray)

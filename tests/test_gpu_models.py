@@ -41,7 +41,7 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-@pytest.mark.parametrize("name,n", [("cfg1", 100), ("cfg3", 48), ("cfg2", 32)])
+@pytest.mark.parametrize("name,n", [("cfg1", 100), ("cfg3", 48), ("cfg2", 32), ("cfg4", 8)])
 @pytest.mark.parametrize("bn", ["identity", "spread"])
 def test_vgg_bit_exact_vs_exact_oracle(name, n, bn):
     cf, model, nodes = build(CONFIGS[name], bn=bn)
@@ -147,6 +147,31 @@ def test_float_activation_types_tolerance(arch, nt):
     assert rel_err(got, o2b) <= 1e-4
 
 
+@pytest.mark.parametrize("nt", ["qnn", "tnn"])
+def test_cfg5_resnet62_small_batch_tolerance(nt):
+    """BASELINE.json configs[4] at its real depth (nres = 10, 63 convolutions) on 8 images: fp32 LeakyReLU activations,
+    so the bar is the north_star tolerance against O1 (float64 accumulation) and O2b; arg-max identical."""
+    cf, model, nodes = build(dict(CONFIGS["cfg5"], network_type=nt), bn="spread")
+    assert model.depth == 62
+    x = images(cf, 8)
+    want, _, info = exact.forward(nodes, x, return_all=True)
+    got, logits = model.predict(x, return_logits=True)
+    assert rel_err(logits, info["logits"]) <= 1e-4
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+    o2b = refstate.forward(nodes, x, trick=False)
+    assert rel_err(got, o2b) <= 1e-4
+
+
+def test_cfg5_integer_twin_full_qnn_resnet62_bit_exact():
+    """Same depth with quantised activations (full-qnn): integer path, bit-exact logits."""
+    cf, model, nodes = build(dict(CONFIGS["cfg5"], network_type="full-qnn"), bn="spread")
+    x = images(cf, 8)
+    want, _, info = exact.forward(nodes, x, return_all=True)
+    got, logits = model.predict(x, return_logits=True)
+    assert np.array_equal(logits, info["logits"])
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+
+
 def test_mnist_resnet_zero_padding_path():
     cf, model, nodes = build(dict(network_type='full-qnn', wbits=4, abits=4, architecture='RESNET', nres=1,
                                   dataset='MNIST', dim=28, channels=1), bn="spread")
@@ -194,6 +219,56 @@ def test_layer_objects_standalone_call():
     assert np.abs(z - want).max() <= 1e-4 * np.abs(want).max()
     with pytest.raises(ValueError):
         QuantizedConv2D(filters=4, kernel_size=3, padding='same')(q.Input(shape=(8, 8, None)))
+
+
+# --------------------------------------------------------------------------- host path: graphs, staleness, pipelining
+def test_layer_set_weights_after_predict_is_not_stale():
+    """The reference idiom ``model.layers[i].set_weights(...)`` (models/model_factory.py:77-105) AFTER a first predict:
+    the captured CUDA graphs and cached BN constants of the plan must be rebuilt, not replayed."""
+    import qnn_b200 as q
+    from qnn_b200 import engine as E
+    cf, model, nodes = build(CONFIGS["cfg3"], bn="spread")
+    x = images(cf, 16)
+    assert np.array_equal(model.predict(x), exact.forward(nodes, x))
+    rng = np.random.default_rng(5)
+    # new kernel for the second conv, new statistics for the first BN -- through the LAYERS, no model-level call
+    conv = [l for l in model.layers if "conv2d" in l.name][1]
+    bn = [l for l in model.layers if isinstance(l, E.BatchNormalization)][0]
+    k2 = rng.uniform(-1, 1, size=conv.kernel.shape).astype(F32)
+    conv.set_weights([k2, conv.bias])
+    g, b, m, v = bn.get_weights()
+    bn.set_weights([g * F32(0.9), b + F32(0.05), m, v * F32(1.1)])
+    from helpers import spec_weights_from_model
+    spec_weights_from_model(model, nodes)
+    want = exact.forward(nodes, x)
+    got = model.predict(x)                       # host path: CUDA-graph slots
+    assert np.array_equal(got, want)
+    got_dev = model.predict(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got_dev, want)
+
+
+def test_predict_async_handles_survive_slot_recycling():
+    """More outstanding handles than pipeline slots, read late and out of order: every handle returns ITS batch."""
+    cf, model, nodes = build(CONFIGS["cfg3"], bn="spread")
+    batches = [images(cf, 8, seed=100 + i) for i in range(8)]
+    handles = [model.predict_async(b) for b in batches]          # PIPELINE_DEPTH = 3 slots, 8 handles
+    for i in (7, 0, 3, 5, 1, 2, 6, 4):
+        assert np.array_equal(handles[i].result().numpy(), exact.forward(nodes, batches[i])), "handle %d" % i
+
+
+def test_many_models_one_process_graph_capture():
+    """A long-lived process that builds model after model (each with its own CUDA-graph slots) must keep capturing:
+    dead plans release their graphs deterministically, and no finaliser runs inside a capture."""
+    import gc
+    want_cache = {}
+    for rep in range(12):
+        name = ("cfg3", "cfg2", "cfg1")[rep % 3]
+        cf, model, nodes = build(CONFIGS[name], bn="spread", seed=rep)
+        x = images(cf, 4 + rep, seed=rep)
+        got = model.predict(x)
+        assert np.array_equal(got, exact.forward(nodes, x))
+        if rep % 4 == 3:
+            gc.collect()
 
 
 # --------------------------------------------------------------------------- trained weights (reference checkpoints)

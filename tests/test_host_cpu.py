@@ -207,3 +207,66 @@ def test_hdf5_reader_on_reference_checkpoint():
     with pytest.raises(ValueError):
         q.reset_names()
         q.build_model(make_cf(architecture="RESNET", nres=5), legacy_resnet=True).load_weights(ref)
+
+
+def test_checkpoint_binding_ignores_absolute_layer_counters():
+    """Keras binds checkpoint layers to model layers in order, not by auto-generated name: a model built after other
+    models in the same process (shifted per-class counters) must load the reference checkpoint identically."""
+    ref = "/root/reference/results/RESNET3/weights_44.hdf5"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkpoints are only present in the build container")
+    q.reset_names()
+    a = q.build_model(make_cf(architecture="RESNET", nres=3), legacy_resnet=True)
+    a.load_weights(ref)
+    # no reset_names(): every auto-generated name of the second model carries a shifted counter
+    q.build_model(make_cf(architecture="RESNET", nres=1), legacy_resnet=True)
+    b = q.build_model(make_cf(architecture="RESNET", nres=3), legacy_resnet=True)
+    assert b.layers[0].name != a.layers[0].name
+    b.load_weights(ref)
+    for wa, wb in zip(a.get_weights(), b.get_weights()):
+        assert np.array_equal(wa, wb)
+    # by_name=True only binds identical names: nothing matches the shifted model, nothing is touched
+    from qnn_b200.hdf5_lite import load_keras_weights
+    c = q.build_model(make_cf(architecture="RESNET", nres=3), legacy_resnet=True)
+    before = [w.copy() for w in c.get_weights()]
+    load_keras_weights(c, ref, by_name=True)
+    assert all(np.array_equal(x, y) for x, y in zip(before, c.get_weights()))
+
+
+def test_plans_do_not_keep_models_alive_and_track_weight_versions():
+    """(i) model -> plan is the only strong edge (no reference cycle: a dropped model frees its plans by reference
+    counting, not whenever the cyclic collector runs); (ii) a per-layer set_weights makes the plan stale."""
+    import gc
+    import weakref
+    from qnn_b200 import engine as E
+    q.reset_names()
+    m = q.build_model(make_cf(**CONFIGS["cfg3"]))
+    plan = m.plan()
+    assert plan.model is m
+    ref_m, ref_p = weakref.ref(m), weakref.ref(plan)
+    gc.disable()
+    try:
+        del plan, m
+        assert ref_m() is None and ref_p() is None, "model/plan survive without the cyclic collector: reference cycle"
+    finally:
+        gc.enable()
+    q.reset_names()
+    m = q.build_model(make_cf(**CONFIGS["cfg3"]))
+    plan = m.plan()
+    plan.steps[0].dev["sentinel"] = object()           # stands for cached device constants / captured graphs
+    plan._sync_weights()
+    assert "sentinel" in plan.steps[0].dev             # nothing changed: caches are kept
+    bn = [l for l in m.layers if isinstance(l, E.BatchNormalization)][0]
+    e0 = E.weights_epoch()
+    bn.set_weights([w + 1 for w in bn.get_weights()])
+    assert E.weights_epoch() == e0 + 1
+    plan._sync_weights()
+    assert "sentinel" not in plan.steps[0].dev         # stale caches dropped
+    conv = m.layers[0]
+    plan.steps[0].dev["sentinel"] = object()
+    conv.set_weights(conv.get_weights())
+    plan._sync_weights()
+    assert "sentinel" not in plan.steps[0].dev
+    # model-level set_weights drops the plans altogether
+    m.set_weights(m.get_weights())
+    assert m.plan() is not plan
