@@ -191,6 +191,25 @@ __device__ __forceinline__ void tmem_ld_wait_dep32(int (&v)[32]) {
       : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two independent IEEE fp32 results per issue slot)
+// The epilogues are instruction-issue bound, so the fixed fp32 pipeline is evaluated on PAIRS of accumulators.
+// Only fma is used: RN(x*s + (-0)) == RN(x*s) and RN(x*1 + a) == RN(x + a) bit for bit (including the sign of
+// zero), and an explicit fma cannot be contracted with its neighbour -- ptxas DOES contract a mul.rn.f32x2 that
+// feeds an add.rn.f32x2 into one FFMA2, which would change the rounding of the fixed op order.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // UMMA shared-memory matrix descriptor, K-major operand whose rows are KC bytes wide and stored with the
 // KC-byte swizzle (KC = 64 or 128): 8-row groups are 8*KC bytes apart (SBO); LBO is unused for swizzled
 // K-major layouts (set to 16 B); version = 1 (Blackwell); layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
@@ -255,15 +274,30 @@ static inline EncodeTiledFn get_encode() {
   return fn;
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 static inline int sm_count() {
-  static int sms = 0;
-  if (!sms) {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of the (function, device) pair: remember per
+// device which size a kernel has been configured for (one static instance per kernel instantiation).
+struct SmemConfigured {
+  int bytes[64] = {0};
+  template <typename K>
+  cudaError_t ensure(K kern, int smem) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64 && bytes[dev] >= smem) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) bytes[dev] = smem;
+    return e;
   }
-  return sms;
-}
+};
 
 
 }  // namespace tcx
