@@ -15,8 +15,8 @@
  *  - all functions return 0 on success, a negative QNNB_E* code otherwise; the message is
  *    available from qnnb_last_error() (thread-local).  Nothing throws across the ABI;
  *  - an unsupported shape is an error, never a silent CPU fallback: there is no CPU path;
- *  - the library allocates no persistent device memory and keeps no global mutable state:
- *    calls are stream-ordered and re-entrant.
+ *  - the compute entry points allocate no device memory and keep no global mutable state:
+ *    calls are stream-ordered and re-entrant (only qnnb_peer_alloc, which exists to allocate, does).
  */
 #ifndef QNNB200_H_
 #define QNNB200_H_
@@ -175,6 +175,22 @@ int qnnb_leaky_f32(const float* x, int64_t count, float alpha, float* y, void* s
 int qnnb_round_f32(const float* x, int64_t count, float* y, void* stream);
 /* int8 levels / packed bits -> fp32 values (level * scale, or +-1) */
 int qnnb_dequantize(int32_t kind, const void* x, int64_t count, int32_t channels, float scale, float* y, void* stream);
+
+/*
+ * NVLink logit path for batch-sharded inference (one process per GPU of one box): the reference evaluates a test set
+ * with one model.predict / model.evaluate over the whole array (test_resnet.py:63-69); sharded over g GPUs the only
+ * exchange is the [N/g, classes] logit block of each shard.  Instead of a collective per step, the gathering rank
+ * exports a device buffer (CUDA IPC) and every other rank maps it and passes `mapped + row offset` as the `y` of its
+ * final qnnb_dense call: the logits cross NVLink / NVSwitch as the kernel's own stores.
+ *   qnnb_peer_alloc : cudaMalloc `bytes` (zero-filled) on the current device, handle = QNNB_PEER_HANDLE_BYTES opaque bytes
+ *   qnnb_peer_open  : map a sibling process's buffer for kernels of the CURRENT device (peer access enabled lazily)
+ *   qnnb_peer_close / qnnb_peer_free : undo open / alloc
+ */
+#define QNNB_PEER_HANDLE_BYTES 64
+int qnnb_peer_alloc(int64_t bytes, void** ptr, void* handle);
+int qnnb_peer_open(const void* handle, void** ptr);
+int qnnb_peer_close(void* ptr);
+int qnnb_peer_free(void* ptr);
 
 /*
  * Profiling aid (not part of the inference path): register a device buffer of `nwords` uint64 (word 0 = event

@@ -78,6 +78,10 @@ PROTOTYPES = {
     "qnnb_leaky_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "qnnb_round_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "qnnb_debug_set_trace": (C.c_int, [C.c_void_p, C.c_int64]),
+    "qnnb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "qnnb_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "qnnb_peer_close": (C.c_int, [C.c_void_p]),
+    "qnnb_peer_free": (C.c_int, [C.c_void_p]),
     "qnnb_dequantize": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
@@ -121,8 +125,32 @@ def current_stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+PEER_HANDLE_BYTES = 64
+
+
+class DeviceBuffer:
+    """A raw device address with a shape -- what a peer-mapped (CUDA IPC) buffer looks like on the ranks that do not
+    own it: kernels may write through it, torch never sees it.  Quacks like a tensor for :func:`ptr`."""
+    is_cuda = True
+
+    def __init__(self, address, shape, dtype):
+        self.address, self.shape, self.dtype = int(address), tuple(int(v) for v in shape), dtype
+
+    def data_ptr(self):
+        return self.address
+
+    def is_contiguous(self):
+        return True
+
+    def rows(self, lo, hi):
+        """Row block [lo, hi) of a 2-D buffer."""
+        import torch
+        width = self.shape[1] * torch.empty((), dtype=self.dtype).element_size()
+        return DeviceBuffer(self.address + lo * width, (hi - lo, self.shape[1]), self.dtype)
+
+
 def ptr(t):
-    """Device pointer of a torch tensor (None -> NULL)."""
+    """Device pointer of a torch tensor or DeviceBuffer (None -> NULL)."""
     if t is None:
         return C.c_void_p(0)
     if not t.is_cuda:

@@ -204,6 +204,8 @@ int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, v
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why);
 bool conv_tc_v1_supported(const qnnb_conv_desc& d);
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
+bool conv_first_tc_shape(const qnnb_conv_desc& d);
+int launch_conv_first_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
 bool conv_f32_tc_supported(const qnnb_conv_desc& d, const char** why);
 int launch_conv_f32_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st);
 void set_trace_buffer(unsigned long long* buf, int cap);

@@ -552,11 +552,8 @@ int launch_th(const CUtensorMap& mx, const CUtensorMap& mr, const CUtensorMap& m
   p.off_bar = up(p.off_c + 3 * F_MAXC * 4, 16);
   const int smem = p.off_bar + 512 + 1024;
   if (smem > 232448) { set_error("conv2d: fp32 tensor-core kernel shared-memory plan overflow (%d B)", smem); return QNNB_EINVAL; }
-  static int configured = 0;                      // largest size this instantiation was configured for
-  if (smem > configured) {
-    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static tcx::SmemConfigured once;                // largest size this instantiation was configured for, per device
+  QNNB_CUDA(once.ensure(kern, smem));
   QNNB_CUDA(launch_pdl(kern, dim3(grid), dim3(F_THREADS), (size_t)smem, st, mx, mr, my, p));
   return QNNB_OK;
 }

@@ -431,6 +431,7 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
+#ifdef QNNB_WITH_V1
 // ------------------------------------------------------------------ K1: the int8 implicit-GEMM kernel
 // TW in {32, 16, 8} selects the pixel-tile geometry {TH, TW, TN}: {8,32,1}, {16,16,1}, {8,8,4}.
 template <int KC, int STAGES, int TW, bool POOL, bool OUT_F32>
@@ -549,6 +550,8 @@ conv3x3_i8_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+#endif  // QNNB_WITH_V1
 
 // ------------------------------------------------------------------ K1 v2: halo-resident implicit GEMM
 // v1 re-fetches the pixel tile once per filter tap (9x the input bytes through L2 -> SMEM), which the timeline
@@ -777,226 +780,10 @@ conv3x3_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   }
 }
 
-// ------------------------------------------------------------------ K5: first layer (uint8 pixels, Cin = 3)
-// Same MMA / TMEM / epilogue machinery, but the channel extent (3 bytes) is too narrow for a TMA box, so four
-// producer warps build the im2col B tile in shared memory themselves.  The RGB rows of the tile's halo are
-// expanded to RGBX words while they are staged, so a pixel's 3x3 patch is nine aligned 32-bit shared loads:
-// K = 9 taps x 4 bytes = 36, padded to 64, which is also exactly the [Cout][9][4] layout K0 packs the kernel in.
-// Both operands use the un-swizzled K-major "interleaved" layout (8 rows x 16 B core matrices, 16-byte K chunks
-// 128 B apart).  The activations are UNSIGNED pixel levels: b_format = u8, a_format = s8.  Global loads of the
-// next tile's halo rows are issued before the current tile is built (software pipelining).
-//
-// G pixel groups: with Cout <= 64 a 128-lane accumulator would be half empty, so G = 2 row blocks of 8 image
-// rows share one tile: B row n = [im2col(pixel n of block 0) | im2col(pixel n of block 1)] (K = 128) and the A
-// tile is block-diagonal (rows 0..63 = W in K bytes 0..63, rows 64..127 = W in K bytes 64..127), which makes
-// D[64 g + c][n] = conv(channel c, pixel n of block g): all 128 lanes and all 8 epilogue warps do useful work.
-constexpr int K5_PRODUCER_WARPS = 4;
-constexpr int K5_PRODUCERS = K5_PRODUCER_WARPS * 32;
-constexpr int K5_THREADS = 128 + NUM_EPI_WARPS * 32 + K5_PRODUCERS;   // 512
-constexpr int K5_KB = 64;                          // K bytes per pixel group (36 used)
-constexpr int K5_ROW_PITCH = 160;                  // bytes per staged halo row: pixel p (-1..32) at byte 16 + 4*p
-
-template <bool POOL, bool OUT_F32, int G>
-struct K5Smem {
-  static constexpr int STAGES = (G == 2) ? 3 : 4;
-  static constexpr int A_BYTES = 2 * TILE_M * K5_KB * G;                 // up to 2 m-tiles (G = 1) or one block-diagonal tile
-  static constexpr int B_BYTES = TILE_N * K5_KB * G;                     // per stage
-  static constexpr int HALO_ROWS = 8 * G + 2;
-  static constexpr int HALO_BYTES = HALO_ROWS * K5_ROW_PITCH;
-  static constexpr int A_OFFSET = 0;
-  static constexpr int B_OFFSET = A_BYTES;
-  static constexpr int HALO_OFFSET = B_OFFSET + STAGES * B_BYTES;
-  static constexpr int STG_OFFSET = (HALO_OFFSET + 2 * HALO_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STG_BYTES = OUT_F32 ? 0 : (POOL ? TILE_N * G / 4 : TILE_N * G) * (TILE_M / G);
-  static constexpr int BAR_OFFSET = STG_OFFSET + 2 * STG_BYTES;          // two staging tiles (store of t overlaps t+1)
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
-};
-
-template <bool POOL, bool OUT_F32, int PITCH, int G, bool SIGN = false>
-__global__ void __launch_bounds__(K5_THREADS, 1)
-conv3x3_u8c3_tc_kernel(const uint8_t* __restrict__ x, const int8_t* __restrict__ wpk, const __grid_constant__ CUtensorMap map_y,
-                       const TcParams p) {
-  constexpr int TW = 32, TH = 8;
-  using SL = K5Smem<POOL, OUT_F32, G>;
-  constexpr int STAGES = SL::STAGES;
-  constexpr bool SPLIT = SPLIT_EPILOGUE && !OUT_F32;   // two staging tiles exist: one per epilogue group
-  constexpr uint32_t SBO = 4 * G * 128;              // bytes between 8-row groups (4G K chunks of 128 B)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sg = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + SL::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + SL::BAR_OFFSET + 8 * (2 * STAGES + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) griddep_launch_dependents();
-  // resident A tile(s): 16-byte K chunk j of row m; G = 1: row = channel, chunks 0..2 = packed words 0..8;
-  // G = 2: row 64 g + c holds channel c's words in chunks 4g..4g+2 and zeros elsewhere (block diagonal)
-  {
-    const int rows = (G == 1) ? p.m_tiles * TILE_M : TILE_M;
-    for (int i = threadIdx.x; i < rows * 4 * G; i += K5_THREADS) {
-      const int j = i % (4 * G);
-      const int row = i / (4 * G);
-      const int ch = (G == 1) ? row : (row % (TILE_M / G));
-      const int g = (G == 1) ? 0 : (row / (TILE_M / G));
-      const int jj = j - 4 * g;                    // chunk index inside this row's own K block
-      uint32_t wd[4] = {0, 0, 0, 0};
-      if (ch < p.cout && jj >= 0 && jj < 4) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(wpk) + (long long)ch * 9;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (4 * jj + b < 9) wd[b] = __ldg(src + 4 * jj + b);
-      }
-      const int mt = row / TILE_M, r = row % TILE_M;
-      *reinterpret_cast<uint4*>(sg + SL::A_OFFSET + mt * (TILE_M * K5_KB * G) + (r >> 3) * SBO + j * 128 + (r & 7) * 16) =
-          make_uint4(wd[0], wd[1], wd[2], wd[3]);
-    }
-  }
-  // zero what the producers never write: the 4th K chunk of every pixel group, and halo pixels -1 and 32
-  for (int i = threadIdx.x; i < STAGES * TILE_N * G; i += K5_THREADS) {
-    const int g = i % G;
-    const int pix = (i / G) % TILE_N;
-    const int st = i / (G * TILE_N);
-    *reinterpret_cast<uint4*>(sg + SL::B_OFFSET + st * SL::B_BYTES + (pix >> 3) * SBO + (4 * g + 3) * 128 + (pix & 7) * 16) =
-        make_uint4(0, 0, 0, 0);
-  }
-  for (int i = threadIdx.x; i < 2 * SL::HALO_ROWS * 2; i += K5_THREADS) {
-    const int row = i >> 1, side = i & 1;
-    *reinterpret_cast<uint32_t*>(sg + SL::HALO_OFFSET + row * K5_ROW_PITCH + (side ? 16 + 4 * 32 : 12)) = 0u;
-  }
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), K5_PRODUCERS); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), SPLIT ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS); }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  fence_proxy_async();                   // A tiles / zero fills were written through the generic proxy
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-  griddep_wait();                        // input images / output buffer only after the previous kernel has completed
-
-  if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {                               // single-threaded role (see tc_ptx.cuh)
-      constexpr uint32_t idesc = make_idesc_i8(TILE_M, TILE_N, /*a signed*/ true, /*b unsigned*/ false);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int mt = tile - fdiv(tile, p.fd_m) * p.m_tiles;
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        trace(p.tr, 4, tile);
-        mbar_wait(full_bar(stage), phase);
-        trace(p.tr, 5, tile);
-        tc_fence_after();
-        const uint64_t a_desc = make_smem_desc_interleaved(smem_base + SL::A_OFFSET + mt * (TILE_M * K5_KB * G), 128, SBO);
-        const uint64_t b_desc = make_smem_desc_interleaved(smem_base + SL::B_OFFSET + stage * SL::B_BYTES, 128, SBO);
-        // K step k covers chunks 2k, 2k+1: advance the start address by 256 B (16 units of 16 B)
-#pragma unroll
-        for (int k = 0; k < 2 * G; ++k)
-          umma_i8(tmem_base + (uint32_t)(acc * TILE_N), a_desc + (uint64_t)(16 * k), b_desc + (uint64_t)(16 * k), idesc, k > 0 ? 1u : 0u);
-        umma_commit(empty_bar(stage));
-        umma_commit(tfull_bar(acc));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
-    epilogue_role_n<TW, POOL, OUT_F32, /*FOLD*/ false, PITCH, G, 0, 2, false, false, SIGN, SPLIT>(p, &map_y, tmem_base, tfull_bar(0), tempty_bar(0),
-                                                                       sg + SL::STG_OFFSET, SL::STG_BYTES, warp, lane);
-  } else if (warp >= 4 + NUM_EPI_WARPS) {
-    // ===================== im2col producers (128 threads) =====================
-    const int t = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
-    // halo staging: work item = (image row hrow of the halo, pixel group of 4 = 3 words)
-    constexpr int ITEMS = SL::HALO_ROWS * 8;
-    constexpr int PER = (ITEMS + K5_PRODUCERS - 1) / K5_PRODUCERS;
-    uint32_t g0[PER], g1[PER], g2[PER];
-    auto issue_loads = [&](int tile) {
-      const int pt = fdiv(tile, p.fd_m);
-      const int nimg = fdiv(pt, p.fd_h);
-      const int th_i = pt - nimg * p.tiles_h;
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const int item = t + u * K5_PRODUCERS;
-        const int hrow = item >> 3, grp = item & 7;
-        const int gh = th_i * (TH * G) - 1 + hrow;
-        g0[u] = g1[u] = g2[u] = 0;
-        if (item < ITEMS && gh >= 0 && gh < p.h) {
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((long long)nimg * p.h + gh) * (TW * 3)) + grp * 3;
-          g0[u] = __ldg(src); g1[u] = __ldg(src + 1); g2[u] = __ldg(src + 2);
-        }
-      }
-    };
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    if (blockIdx.x < p.num_tiles) issue_loads(blockIdx.x);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      uint8_t* halo = sg + SL::HALO_OFFSET + (it & 1) * SL::HALO_BYTES;
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const int item = t + u * K5_PRODUCERS;
-        if (item < ITEMS) {
-          // 12 RGB bytes -> 4 RGBX words
-          const uint32_t p0 = g0[u] & 0x00FFFFFFu;
-          const uint32_t p1 = (g0[u] >> 24) | ((g1[u] & 0x0000FFFFu) << 8);
-          const uint32_t p2 = (g1[u] >> 16) | ((g2[u] & 0x000000FFu) << 16);
-          const uint32_t p3 = g2[u] >> 8;
-          *reinterpret_cast<uint4*>(halo + (item >> 3) * K5_ROW_PITCH + 16 + (item & 7) * 16) = make_uint4(p0, p1, p2, p3);
-        }
-      }
-      named_bar_sync(1, K5_PRODUCERS);
-      if (t == 0) trace(p.tr, 10, tile);             // producer: halo staged
-      if (tile + (int)gridDim.x < p.num_tiles) issue_loads(tile + gridDim.x);      // prefetch the next tile's rows
-      mbar_wait_parked(empty_bar(stage), phase ^ 1u);
-      uint8_t* btile = sg + SL::B_OFFSET + stage * SL::B_BYTES;
-#pragma unroll
-      for (int q = 0; q < 2 * G; ++q) {
-        const int gpix = t + q * K5_PRODUCERS;       // pixel of the (8G x 32) tile
-        const int g = gpix >> 8;                     // pixel group = 8-row block
-        const int pix = gpix & 255;                  // accumulator column
-        const int th = gpix >> 5, tw = gpix & 31;
-        uint32_t k[12];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const uint32_t* hp = reinterpret_cast<const uint32_t*>(halo + (th + r) * K5_ROW_PITCH + 12) + tw;   // pixel tw-1
-          k[3 * r + 0] = hp[0]; k[3 * r + 1] = hp[1]; k[3 * r + 2] = hp[2];
-        }
-        k[9] = k[10] = k[11] = 0;
-        uint4* dst = reinterpret_cast<uint4*>(btile + (pix >> 3) * SBO + (4 * g) * 128 + (pix & 7) * 16);
-        dst[0] = make_uint4(k[0], k[1], k[2], k[3]);
-        dst[8] = make_uint4(k[4], k[5], k[6], k[7]);
-        dst[16] = make_uint4(k[8], k[9], k[10], k[11]);
-      }
-      fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(full_bar(stage));
-      if (t == 0) trace(p.tr, 3, tile);              // producer: im2col tile published
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ------------------------------------------------------------------ host side
 struct Geometry { int tw, th, tn; };
 
+#ifdef QNNB_WITH_V1
 bool pick_geometry(int h, int w, Geometry* g) {
   if (w == 32 && h % 8 == 0) { *g = {32, 8, 1}; return true; }
   if (w == 16 && h % 16 == 0) { *g = {16, 16, 1}; return true; }
@@ -1021,11 +808,8 @@ int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorM
   auto kern = conv3x3_i8_tc_kernel<KC, STAGES, TW, POOL, OUT_F32>;
   constexpr int smem = SmemLayout<KC, STAGES, POOL, OUT_F32>::TOTAL;
   static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;                 // per template instantiation
-  if (!configured) {
-    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemConfigured once;                     // per template instantiation, keyed by device inside
+  QNNB_CUDA(once.ensure(kern, smem));
   kern<<<grid, NUM_THREADS, smem, st>>>(mw, mx, my, p);
   QNNB_CUDA(cudaGetLastError());
   return QNNB_OK;
@@ -1045,6 +829,8 @@ int launch_kc(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& m
   return launch_tw<KC, STAGES, 8>(mw, mx, my, p, grid, pool, f32, st);
 }
 
+#endif  // QNNB_WITH_V1
+
 bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
   if (d.epi.res_kind != QNNB_KIND_NONE) { *why = "residual epilogue not on the tensor-core path"; return false; }
   if (d.epi.act == QNNB_ACT_QUANT || d.epi.act == QNNB_ACT_SIGN_I8) return true;
@@ -1053,81 +839,14 @@ bool epilogue_ok(const qnnb_conv_desc& d, const char** why) {
   return false;
 }
 
-bool first_layer_shape(const qnnb_conv_desc& d) {
-  return d.in_kind == QNNB_KIND_U8 && d.cin == 3 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.w == 32 && d.h % 8 == 0 &&
-         d.cout <= 256 && d.cout % 32 == 0;
-}
-
-int launch_first_layer(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
-  EncodeTiledFn encode = get_encode();
-  if (!encode) { set_error("conv2d: cuTensorMapEncodeTiled is not available from the driver"); return QNNB_ECUDA; }
-  const bool pool = d.epi.pool == 2;
-  const bool f32 = d.epi.act == QNNB_ACT_NONE;
-  // two pixel groups per tile when the accumulator lanes would otherwise be half empty
-  const int G = (!f32 && d.cout == 64 && d.h % 16 == 0) ? 2 : 1;
-  TcParams p;
-  p.tr = g_trace;
-  p.n = d.n; p.h = d.h; p.w = d.w; p.cin = d.cin; p.cout = d.cout;
-  p.tiles_w = 1;
-  p.tiles_h = d.h / (8 * G);
-  p.tiles_n = d.n;
-  p.m_tiles = (G == 2) ? 1 : ceil_div(d.cout, TILE_M);
-  p.num_tiles = p.tiles_h * p.tiles_n * p.m_tiles;
-  p.fd_m = make_fastdiv(p.m_tiles); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h);
-  p.kchunks = 1;
-  p.resident = 0;
-  p.out_pitch = d.cout < TILE_M ? d.cout : TILE_M;
-  p.y = y;
-  p.epi = make_epi(d.epi);
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  CUtensorMap my;
-  memset(&my, 0, sizeof(my));
-  if (!f32) {
-    Geometry g = {32, 8 * G, 1};
-    int rc = make_output_map(encode, &my, y, d.n, pool ? d.h / 2 : d.h, pool ? d.w / 2 : d.w, d.cout, p.out_pitch, g, pool);
-    if (rc) return rc;
-  }
-  auto go = [&](auto kern, int smem) -> int {
-    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    QNNB_CUDA(launch_pdl(kern, dim3(grid), dim3(K5_THREADS), (size_t)smem, st, (const uint8_t*)x, (const int8_t*)w, my, p));
-    return QNNB_OK;
-  };
-  if (f32) return go(conv3x3_u8c3_tc_kernel<false, true, 0, 1>, K5Smem<false, true, 1>::TOTAL);
-  if (d.epi.act == QNNB_ACT_SIGN_I8) {
-    if (G == 2) {
-      if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64, 2, true>, K5Smem<true, false, 2>::TOTAL);
-      return go(conv3x3_u8c3_tc_kernel<false, false, 64, 2, true>, K5Smem<false, false, 2>::TOTAL);
-    }
-    if (p.out_pitch == 128) {
-      if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 128, 1, true>, K5Smem<true, false, 1>::TOTAL);
-      return go(conv3x3_u8c3_tc_kernel<false, false, 128, 1, true>, K5Smem<false, false, 1>::TOTAL);
-    }
-    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 0, 1, true>, K5Smem<true, false, 1>::TOTAL);
-    return go(conv3x3_u8c3_tc_kernel<false, false, 0, 1, true>, K5Smem<false, false, 1>::TOTAL);
-  }
-  if (G == 2) {
-    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 64, 2>, K5Smem<true, false, 2>::TOTAL);
-    return go(conv3x3_u8c3_tc_kernel<false, false, 64, 2>, K5Smem<false, false, 2>::TOTAL);
-  }
-  if (p.out_pitch == 128) {
-    if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 128, 1>, K5Smem<true, false, 1>::TOTAL);
-    return go(conv3x3_u8c3_tc_kernel<false, false, 128, 1>, K5Smem<false, false, 1>::TOTAL);
-  }
-  if (pool) return go(conv3x3_u8c3_tc_kernel<true, false, 0, 1>, K5Smem<true, false, 1>::TOTAL);
-  return go(conv3x3_u8c3_tc_kernel<false, false, 0, 1>, K5Smem<false, false, 1>::TOTAL);
-}
-
 // ---- v2 (halo-resident) launch
 template <int KC, int TH, bool POOL, bool OUT_F32, bool SIGN = false>
 int launch_v2_variant(const CUtensorMap& mw, const CUtensorMap& mx, const CUtensorMap& my, const TcParams& p, int grid, cudaStream_t st) {
   auto kern = conv3x3_i8_tc2_kernel<KC, TH, POOL, OUT_F32, SIGN>;
   constexpr int smem = Smem2<KC, TH, POOL, OUT_F32>::TOTAL;
   static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    QNNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemConfigured once;                     // per template instantiation, keyed by device inside
+  QNNB_CUDA(once.ensure(kern, smem));
   QNNB_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)smem, st, mw, mx, my, p));
   return QNNB_OK;
 }
@@ -1225,15 +944,20 @@ void set_trace_buffer(unsigned long long* buf, int cap) { g_trace.buf = buf; g_t
 unsigned long long* get_trace_buffer() { return g_trace.buf; }
 
 bool conv_tc_v1_supported(const qnnb_conv_desc& d) {
+#ifdef QNNB_WITH_V1
   Geometry g;
   return d.in_kind == QNNB_KIND_I8 && d.epi.act != QNNB_ACT_SIGN_I8 && pick_geometry(d.h, d.w, &g);
+#else
+  (void)d;
+  return false;
+#endif
 }
 
 bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
   Geometry g;
   // tile indices must stay below 2^24 (FastDiv): at most 8 tiles per image on any supported shape
   if ((long long)d.n * ((d.h + 7) / 8) * ((d.w + 7) / 8) * ((d.cout + 127) / 128) >= (1ll << 24)) { *why = "batch too large for one launch"; return false; }
-  if (first_layer_shape(d)) return epilogue_ok(d, why);
+  if (conv_first_tc_shape(d)) return epilogue_ok(d, why);
   if (d.in_kind != QNNB_KIND_I8) { *why = "input must be int8 levels (or uint8 32-wide RGB for the first layer)"; return false; }
   if (d.kh != 3 || d.kw != 3 || d.stride != 1) { *why = "only 3x3 stride 1"; return false; }
   if (d.cin % 64 != 0 || d.cin > 256) { *why = "Cin must be 64, 128, 192 or 256"; return false; }
@@ -1244,7 +968,13 @@ bool conv_tc_supported(const qnnb_conv_desc& d, const char** why) {
 }
 
 int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* y, cudaStream_t st) {
-  if (first_layer_shape(d)) return launch_first_layer(d, x, w, y, st);
+  if (conv_first_tc_shape(d)) return launch_conv_first_tc(d, x, w, y, st);
+#ifndef QNNB_WITH_V1
+  // production build: the halo-resident kernel serves every supported shape (the first-generation kernel -- one TMA
+  // box per filter tap -- is only compiled with -DQNNB_WITH_V1 for A/B profiling)
+  if (d.impl == QNNB_IMPL_TCGEN05_V1) { set_error("conv2d: this build does not contain the v1 kernel (make EXTRA=-DQNNB_WITH_V1)"); return QNNB_EUNSUPPORTED; }
+  return launch_conv_tc_v2(d, x, w, y, st);
+#else
   // Kernel choice (measured on B200, profiles/): the halo-resident kernel wins when a tile is one 32-row block
   // (one N = 256 MMA per tap: 32-row maps, -8..-20 %); with 16- or 8-row maps it needs N = 128 / 64 MMAs that re-read
   // the weight tile from shared memory per image and becomes SMEM-bandwidth bound, so v1 keeps those shapes.
@@ -1304,6 +1034,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   if (KC == 128) return launch_kc<128, 4>(mw, mx, my, p, grid, g.tw, pool, f32, st);
   return launch_kc<64, 6>(mw, mx, my, p, grid, g.tw, pool, f32, st);
+#endif
 }
 
 }  // namespace qnnb

@@ -95,6 +95,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): dst, src 16-byte aligned, bytes a multiple of 16; completes on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -208,6 +213,24 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
+}
+
+// tcgen05.wait::ld that "redefines" the destination registers of two earlier 16-column loads
+__device__ __forceinline__ void tmem_ld_wait_dep16x2(int (&a)[16], int (&b)[16]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]),
+        "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]),
+        "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]),
+        "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+      :
+      : "memory");
+}
+
+// ... and of four (64 accumulators requested at once)
+__device__ __forceinline__ void tmem_ld_wait_dep16x4(int (&a)[16], int (&b)[16], int (&c)[16], int (&d)[16]) {
+  tmem_ld_wait_dep16x2(a, b);            // the first wait covers every load issued so far; the second only pins c, d
+  tmem_ld_wait_dep16x2(c, d);
 }
 
 // UMMA shared-memory matrix descriptor, K-major operand whose rows are KC bytes wide and stored with the

@@ -174,6 +174,8 @@ def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=Fa
     dev = x.data.device
     if out is None:
         out = torch.empty((n, units), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (n, int(units)) or out.dtype != torch.float32:
+        raise ValueError("dense: bad output buffer %s/%s, need %s/float32" % (tuple(out.shape), out.dtype, (n, int(units))))
     if softmax and want_logits and logits is None:
         logits = torch.empty((n, units), dtype=torch.float32, device=dev)
     L.check(L.lib().qnnb_dense(C.byref(d), L.ptr(x.data), L.ptr(w_packed), L.ptr(out),

@@ -324,7 +324,13 @@ class Plan:
             inv, shift = self._bn_dev(st, st.bn, dev)
         epi = K.make_epilogue(scale, bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift)
         xin = K.QTensor(x.kind, x.data.reshape(n, -1), x.scale, fin if x.kind != "b1" else fin)
-        out, logits = K.dense(xin, wp, lay.units, epi, softmax=st.softmax, want_logits=st.softmax, avg_positions=avg_positions)
+        # the caller's output buffer (Plan.forward(out=...): e.g. a peer-mapped block of the gathering rank) takes the
+        # network output directly when this layer produces it
+        dst = env.get("out_buffer") if st.out == self.output_idx else None
+        out, logits = K.dense(xin, wp, lay.units, epi, softmax=st.softmax, want_logits=st.softmax, avg_positions=avg_positions,
+                              out=dst)
+        if dst is not None:
+            env["out_buffer_used"] = True
         env[st.out] = K.QTensor("f32", out, 1.0, lay.units)
         if logits is not None:
             env["logits"] = logits
@@ -342,16 +348,22 @@ class Plan:
             env[st.out] = y if isinstance(y, K.QTensor) else K.as_qtensor(y)
             self.launches += 1
 
-    def run(self, x) -> dict:
+    def run(self, x, out=None) -> dict:
         """One forward over a device batch.  Returns the environment (tensor index -> QTensor)."""
         self._sync_weights()
         env = {self.input_idx: K.as_qtensor(x)}
+        if out is not None:
+            env["out_buffer"] = out
         for st in self.steps:
             self.run_step(st, env)
+        if out is not None and not env.get("out_buffer_used"):
+            raise ValueError("plan: the network output is not produced by a dense layer; out= is not supported here")
         return env
 
-    def forward(self, x, return_logits=False):
-        env = self.run(x)
+    def forward(self, x, return_logits=False, out=None):
+        """``out``: optional [N, units] fp32 destination of the network output (a CUDA tensor or an
+        ``_lib.DeviceBuffer``, e.g. ``sharding.PeerGather.block()``), written by the final dense kernel itself."""
+        env = self.run(x, out=out)
         out = env[self.output_idx]
         out = out.data if out.kind == "f32" else out.to_float()
         if return_logits:

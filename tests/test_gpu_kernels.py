@@ -334,6 +334,24 @@ TC_CASES_V2_ONLY = [
 ]
 
 
+import functools  # noqa: E402
+
+
+@functools.lru_cache(maxsize=None)
+def _has_v1():
+    """Does the loaded library contain the v1 kernel?  (A production build answers QNNB_EUNSUPPORTED for any v1 request.)"""
+    q, L, K = _mods()
+    x = K.QTensor("i8", torch.zeros((1, 8, 32, 64), dtype=torch.int8, device="cuda"), 0.125, 64)
+    wp = torch.zeros((128, 3, 3, 64), dtype=torch.int8, device="cuda")
+    try:
+        K.conv2d(x, wp, 3, 3, 128, 1, K.make_epilogue(1.0, act=L.ACT_NONE), impl=L.IMPL_TCGEN05_V1)
+        return True
+    except L.QnnbError as exc:
+        if exc.code == L.EUNSUPPORTED:
+            return False
+        raise
+
+
 @pytest.mark.parametrize("impl", ["v2", "v1"])
 @pytest.mark.parametrize("case", TC_CASES + TC_CASES_V2_ONLY, ids=["n%d_%dx%d_%d-%d_w%da%d%s%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_pool" if c[7] else "", "_f32" if c[8] else "") for c in TC_CASES + TC_CASES_V2_ONLY])
 def test_conv2d_tcgen05_bit_exact(case, impl):
@@ -341,6 +359,8 @@ def test_conv2d_tcgen05_bit_exact(case, impl):
     if impl == "v1" and case in TC_CASES_V2_ONLY:
         pytest.skip("shape only covered by the halo-resident kernel")
     IMPL = L.IMPL_TCGEN05 if impl == "v2" else L.IMPL_TCGEN05_V1
+    if impl == "v1" and not _has_v1():
+        pytest.skip("production build: the first-generation kernel is only compiled with make EXTRA=-DQNNB_WITH_V1")
     n, h, w, cin, cout, nb, abits, pool, f32_out = case
     rng = np.random.default_rng(_seed(case))
     x, xs = _rand_input(rng, "i8", (n, h, w, cin), abits)

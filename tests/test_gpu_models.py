@@ -121,6 +121,53 @@ def test_vgg_teacher_forced_vs_reference_with_scaling_identity():
     assert rel_err(got, out) <= 1e-5
 
 
+def test_forward_into_caller_buffer_and_peer_block():
+    """Plan.forward(out=...) -- the hook of the NVLink logit path: the final dense kernel writes the network output
+    into the caller's buffer (a tensor, or a raw device address as sharding.PeerGather hands out)."""
+    from qnn_b200 import _lib as L
+    cf, model, nodes = build(CONFIGS["cfg3"])
+    x = images(cf, 16)
+    want = exact.forward(nodes, x)
+    plan = model.plan()
+    xd = torch.from_numpy(x).cuda()
+    ring = torch.full((3 * 16, 10), -7.0, dtype=torch.float32, device="cuda")
+    ret = plan.forward(xd, out=ring[16:32])
+    torch.cuda.synchronize()
+    assert ret.data_ptr() == ring[16:32].data_ptr()
+    assert np.array_equal(ring[16:32].cpu().numpy(), want)
+    assert float(ring[:16].max()) == -7.0 and float(ring[32:].max()) == -7.0
+    raw = L.DeviceBuffer(ring.data_ptr(), ring.shape, torch.float32)
+    plan.forward(xd, out=raw.rows(32, 48))
+    torch.cuda.synchronize()
+    assert np.array_equal(ring[32:].cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        plan.forward(xd, out=ring[:8])
+
+
+def test_peer_gather_root_side(tmp_path):
+    """sharding.PeerGather on its owning rank (world of one): exported buffer, per-slot blocks, torch view."""
+    import torch.distributed as dist
+    from qnn_b200.sharding import PeerGather
+    cf, model, nodes = build(CONFIGS["cfg3"])
+    x = images(cf, 8)
+    want = exact.forward(nodes, x)
+    started = not dist.is_initialized()
+    if started:
+        dist.init_process_group("gloo", init_method="file://%s" % (tmp_path / "rdzv"), world_size=1, rank=0)
+    try:
+        pg = PeerGather(8, 10, slots=3)
+        plan = model.plan()
+        xd = torch.from_numpy(x).cuda()
+        plan.forward(xd, out=pg.block(2))
+        pg.fence()
+        assert np.array_equal(pg.gathered(2).cpu().numpy(), want)
+        assert float(pg.gathered(0).abs().max()) == 0.0 and float(pg.gathered(1).abs().max()) == 0.0
+        pg.close()
+    finally:
+        if started:
+            dist.destroy_process_group()
+
+
 @pytest.mark.parametrize("nt,legacy", [("full-qnn", False), ("full-qnn", True), ("full-bnn", False), ("qbnn", False), ("qtnn", False)])
 def test_resnet_integer_types_bit_exact(nt, legacy):
     cf, model, nodes = build(dict(network_type=nt, wbits=4, abits=4, architecture='RESNET', nres=2), bn="spread",

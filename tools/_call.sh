@@ -1,7 +1,7 @@
-mkdir -p /tmp/ncu
-B="python bench.py --workload cfg5 --steps 2 --warmup 3 --graphs 0 --streams 1 --no-cpu-baseline"
-$B > gpurun_out/y_plain_cfg5.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/y_launches_cfg5.csv $B > /tmp/ncu/l.log 2>&1
-$B > /tmp/ncu/plain.log 2>&1 && ncu --set full --clock-control none -k regex:'conv|dense' -s 192 -c 12 -o /tmp/ncu/prof_cfg5 -f $B > /tmp/ncu/full.log 2>&1
-python tools/ncu_summary.py /tmp/ncu/prof_cfg5.ncu-rep gpurun_out/y_ncu_cfg5.csv
-rm -rf /tmp/ncu
-ls -la gpurun_out/y_*
+python -m pytest tests -m gpu -x -q -k "first_layer or vgg_bit_exact" > gpurun_out/r2j_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2j_tests.log
+tail -3 gpurun_out/r2j_tests.log
+for n in 296 1036 2072; do python tools/k5_probe.py $n 64 1 4; done 2>&1 | tee gpurun_out/r2j_k5.log
+python tools/k5_probe.py 256 64 1 1 2>&1 | tee -a gpurun_out/r2j_k5.log
+export QNNB_LIB=$PWD/quantizedneuralnetworks-keras-tensorflow_b200/libqnnb200_trace.so
+export TRACE_WARPS=0,1,9,17 TRACE_TILES=9
+python tools/k5_trace.py 1036 64 1 4 > gpurun_out/r2j_trace0.log 2>&1

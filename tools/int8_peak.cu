@@ -183,6 +183,41 @@ void run(const char* name, int groups, int reps, int sms, int smem) {
     fprintf(stderr, "layout %s: burst %.1f TOP/s, sustained %.1f TOP/s\n", name, ops / (best * 1e-3) / 1e12, ops / (total * 1e-3) / 1e12);
 }
 
+// In-process entry (bench.py loads tools/libint8peak.so with ctypes): the SWIZZLE_128B measurement only, on the current
+// device and its primary context.  Returns 0 on success.
+extern "C" int qnnb_int8_peak(int groups, int reps, double* burst_tops, double* sustained_tops) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int smem = 2 * (128 + 256) * 128 + 1024;
+  if (cudaFuncSetAttribute(peak_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  peak_kernel<0><<<sms, 128, smem>>>(groups, 1u);
+  if (cudaDeviceSynchronize() != cudaSuccess) return 3;
+  double best = 1e30;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0);
+    peak_kernel<0><<<sms, 128, smem>>>(groups, 2u + r);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventRecord(e0);
+  for (int r = 0; r < reps * 4; ++r) peak_kernel<0><<<sms, 128, smem>>>(groups, 100u + r);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms_all; cudaEventElapsedTime(&ms_all, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess) return 4;
+  const double ops = (double)sms * groups * 16.0 * 2.0 * 128 * 256 * 32;
+  if (burst_tops) *burst_tops = ops / (best * 1e-3) / 1e12;
+  if (sustained_tops) *sustained_tops = ops / ((double)ms_all / (reps * 4) * 1e-3) / 1e12;
+  return 0;
+}
+
+#ifndef QNNB_PEAK_LIB
 int main(int argc, char** argv) {
   int groups = argc > 1 ? atoi(argv[1]) : 4000;
   int reps = argc > 2 ? atoi(argv[2]) : 20;
@@ -202,3 +237,4 @@ int main(int argc, char** argv) {
   run<0>("SWIZZLE_128B", groups, reps, sms, smem);
   return 0;
 }
+#endif
