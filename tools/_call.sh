@@ -1,7 +1,4 @@
-python -m pytest tests -m gpu -x -q -k "first_layer or vgg_bit_exact" > gpurun_out/r2j_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2j_tests.log
-tail -3 gpurun_out/r2j_tests.log
-for n in 296 1036 2072; do python tools/k5_probe.py $n 64 1 4; done 2>&1 | tee gpurun_out/r2j_k5.log
-python tools/k5_probe.py 256 64 1 1 2>&1 | tee -a gpurun_out/r2j_k5.log
-export QNNB_LIB=$PWD/quantizedneuralnetworks-keras-tensorflow_b200/libqnnb200_trace.so
-export TRACE_WARPS=0,1,9,17 TRACE_TILES=9
-python tools/k5_trace.py 1036 64 1 4 > gpurun_out/r2j_trace0.log 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/t1_tests.log 2>&1; echo "rc=$?" >> gpurun_out/t1_tests.log
+tail -5 gpurun_out/t1_tests.log
+python bench.py --streams 1 --no-secondary --no-cpu-baseline > gpurun_out/t1_cfg3_s1.log 2>gpurun_out/t1_cfg3_s1.err; tail -1 gpurun_out/t1_cfg3_s1.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['per_kernel_ms'])"
+python bench.py > gpurun_out/t1_default.log 2>gpurun_out/t1_default.err; tail -1 gpurun_out/t1_default.log | cut -c1-600
