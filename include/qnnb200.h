@@ -177,6 +177,40 @@ int qnnb_round_f32(const float* x, int64_t count, float* y, void* stream);
 int qnnb_dequantize(int32_t kind, const void* x, int64_t count, int32_t channels, float scale, float* y, void* stream);
 
 /*
+ * Whole-network launch for the small VGG nets: every layer of models/vgg.py:15-42 -- first conv on the uint8 image,
+ * (conv -> BatchNormalization -> Activation [-> MaxPooling2D]) x nconv, Flatten, Fc, BatchNormalization -- in ONE
+ * kernel; an image stays in one SM's shared memory from the input bytes to the logits (csrc/net_fused.cu).  Covers
+ * nets whose packed kernels and activation maps fit there: images up to 32x32 with 1 or 3 channels, 3x3 stride-1
+ * convolutions with 32 or 64 filters, quantized_tanh / binary_tanh activations kept as int8 levels, <= 21 units.
+ * Same arithmetic as the per-layer entry points (bit-identical results).
+ *   conv[l].w   : packed by qnnb_pack_weights (QNNB_WFMT_I8), cin = image channels (l = 0) or conv[l-1].cout
+ *   conv[l].epi : acc_scale, bias, bn_inv / bn_shift, act (QNNB_ACT_QUANT + abits | QNNB_ACT_SIGN_I8); `pool` of the
+ *                 epilogue is ignored in favour of conv[l].pool
+ *   dense_w     : packed 1x1 kernel [units][fin], fin = (final map) h * w * cout in Flatten (HWC) order
+ *   x : uint8 [n][h][w][cin], 16-byte aligned;  y : float [n][units]
+ */
+#define QNNB_NET_MAX_CONVS 6
+typedef struct qnnb_net_conv {
+  int32_t       cout;
+  int32_t       pool;       /* 0 | 2 */
+  const void*   w;
+  qnnb_epilogue epi;
+} qnnb_net_conv;
+
+typedef struct qnnb_vgg_desc {
+  int32_t       n, h, w, cin;
+  int32_t       nconv;
+  qnnb_net_conv conv[QNNB_NET_MAX_CONVS];
+  int32_t       units;
+  const void*   dense_w;
+  qnnb_epilogue dense_epi;  /* act NONE */
+} qnnb_vgg_desc;
+
+/* 1 when qnnb_vgg_forward covers this net, else 0 (the host then runs the per-layer plan) */
+int qnnb_vgg_forward_supported(const qnnb_vgg_desc* desc);
+int qnnb_vgg_forward(const qnnb_vgg_desc* desc, const void* x, float* y, void* stream);
+
+/*
  * NVLink logit path for batch-sharded inference (one process per GPU of one box): the reference evaluates a test set
  * with one model.predict / model.evaluate over the whole array (test_resnet.py:63-69); sharded over g GPUs the only
  * exchange is the [N/g, classes] logit block of each shard.  Instead of a collective per step, the gathering rank

@@ -60,6 +60,24 @@ class DenseDesc(C.Structure):
     ]
 
 
+NET_MAX_CONVS = 6
+
+
+class NetConv(C.Structure):
+    _fields_ = [("cout", C.c_int32), ("pool", C.c_int32), ("w", C.c_void_p), ("epi", Epilogue)]
+
+
+class VggDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32),
+        ("nconv", C.c_int32),
+        ("conv", NetConv * NET_MAX_CONVS),
+        ("units", C.c_int32),
+        ("dense_w", C.c_void_p),
+        ("dense_epi", Epilogue),
+    ]
+
+
 # name -> (restype, argtypes); the CPU test-suite checks this table against the header
 PROTOTYPES = {
     "qnnb_version": (C.c_int, []),
@@ -72,6 +90,8 @@ PROTOTYPES = {
     "qnnb_conv2d_tc_supported": (C.c_int, [C.POINTER(ConvDesc)]),
     "qnnb_conv2d_out_shape": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qnnb_dense": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qnnb_vgg_forward_supported": (C.c_int, [C.POINTER(VggDesc)]),
+    "qnnb_vgg_forward": (C.c_int, [C.POINTER(VggDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_quantize_act": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "qnnb_batchnorm_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_maxpool2_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

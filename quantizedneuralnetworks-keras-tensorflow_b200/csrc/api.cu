@@ -150,4 +150,26 @@ int qnnb_dense(const qnnb_dense_desc* d, const void* x, const void* w, float* y,
   return launch_dense(*d, x, w, y, logits, (cudaStream_t)stream);
 }
 
+int qnnb_vgg_forward_supported(const qnnb_vgg_desc* d) {
+  if (!d) return 0;
+  const char* why = "";
+  return vgg_fused_supported(*d, &why) ? 1 : 0;
+}
+
+int qnnb_vgg_forward(const qnnb_vgg_desc* d, const void* x, float* y, void* stream) {
+  QNNB_CHECK_ARG(d, "vgg_forward: null descriptor");
+  QNNB_CHECK_ARG(d->n >= 0, "vgg_forward: bad batch size %d", d->n);
+  QNNB_CHECK_ARG(d->nconv >= 1 && d->nconv <= QNNB_NET_MAX_CONVS, "vgg_forward: nconv=%d outside 1..%d", d->nconv, QNNB_NET_MAX_CONVS);
+  for (int l = 0; l < d->nconv; ++l) {
+    int rc = validate_epilogue(d->conv[l].epi, true, false);
+    if (rc) return rc;
+  }
+  int rc = validate_epilogue(d->dense_epi, false, false);
+  if (rc) return rc;
+  QNNB_CHECK_ARG(d->dense_epi.act == QNNB_ACT_NONE, "vgg_forward: the dense head has no activation (act=%d)", d->dense_epi.act);
+  if (d->n == 0) return QNNB_OK;
+  QNNB_CHECK_ARG(x && y, "vgg_forward: null pointer");
+  return launch_vgg_fused(*d, x, y, (cudaStream_t)stream);
+}
+
 }  // extern "C"

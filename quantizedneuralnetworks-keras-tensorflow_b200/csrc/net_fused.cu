@@ -1,0 +1,506 @@
+// Kf -- whole-network kernel for the small VGG nets: ONE launch runs every layer of models/vgg.py:15-42
+//   [QuantizedConv2D | BinaryConv2D] -> BatchNormalization -> Activation [-> MaxPooling2D] ... -> Flatten -> Fc -> BN
+// (layers/quantized_layers.py:164-194, layers/binary_layers.py:160-187 for the convolutions; :79-88 / :78-85 for the
+// dense head) for the configurations whose packed kernels fit in one SM's shared memory (<= 64 filters per layer:
+// BASELINE config 1, the MNIST 28x28x1 64/64/64 net, and the CIFAR-10 64/64/64 variant of config/config_CIFAR-10.py).
+//
+// Why: as separate layer kernels such a net is pure launch latency and fill / drain -- cfg1 took 61 us for 100 images
+// (four launches of ~15 us on 100 x 9.5 M MACs), 0.5 % of any roofline.  Here one persistent CTA takes an IMAGE through
+// the whole net: the activations never leave the SM, the kernels of all layers stay resident as UMMA A operands, and
+// the only global traffic is the image in (one bulk copy) and `units` floats out.
+//
+//   * Activations live in shared memory in the un-swizzled K-major core-matrix layout, one "raster" per layer:
+//     [channel / 16][pixel of the zero-haloed map, pitch W + 2][16 channels] -- pixel p of a plane sits at byte 16 p,
+//     which is exactly the row pitch of an 8 x 16 B core matrix, so the B operand of filter tap (r, s) is THE SAME
+//     raster seen through a descriptor whose start address is shifted by (r * pitch + s) pixels (no im2col, any map
+//     width; the two halo columns between image rows produce two garbage accumulator columns per row, never read).
+//   * conv l >= 1: per block of image rows 9 taps x Cin/32 tcgen05.mma.kind::i8 (M 128 of which `cout` rows are kernel
+//     rows, N = rows x pitch <= 256, K 32), int32 accumulators in TMEM, two 256-column buffers (MMA of block b + 1
+//     overlaps the epilogue of block b).  First layer (Cin 1 or 3, K = 9 Cin <= 27): an explicit 32-byte im2col row
+//     per pixel, ONE MMA per block, u8 x s8.
+//   * Epilogue: thread = output channel (TMEM lane), 8 warps (the lane quarters that hold the <= 64 kernel rows), four
+//     warp pairs take alternate image-row pairs of a block.  2x2 max-pool on the raw accumulators (min where the BN slope
+//     is negative), then the fixed fp32 op order of common.cuh (qaffine / quant_scaled, or the binary_tanh threshold),
+//     and the level byte goes straight into the NEXT layer's raster (or the flat HWC feature vector of the dense head).
+//   * Warp roles (512 threads): warps with (id % 4) < 2 -> epilogue; warp 2 -> one elected MMA-issuing thread; the other
+//     seven -> image fetch (bulk copy, double buffered), first-layer im2col of the NEXT image while this one is in
+//     flight, and the dense head (dp4a + warp reduce, fp32 affine) of the PREVIOUS image.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <string.h>
+
+namespace qnnb {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int NF_THREADS = 512;
+constexpr int NF_MAXL = QNNB_NET_MAX_CONVS;
+constexpr int NF_ABLK = 2048;            // one A block: 64 kernel rows x 32 K bytes (the MMA reads 128 rows: the next block)
+constexpr int NF_WORKERS = 7;            // worker warps
+constexpr int NF_SMEM_MAX = 232448;
+
+struct NfLayer {
+  int h, w, cin, cout;
+  int wp;                  // input pitch in pixels (layer 0: w, the im2col rows; else w + 2)
+  int rb, nblk;            // image rows per block, blocks
+  int pool, sign;
+  int in_off, in_plane;    // bytes: operand base, distance between 16-channel planes (K chunks)
+  int out_off, out_plane, out_wp;      // next raster; out_plane == 0: flat [pixel][cout] feature vector
+  int a_off;               // A blocks of this layer
+  int cin_pad;             // channel pitch of the packed kernel
+  float qm, acc_scale;
+  const int8_t* wpk;
+  const float *bias, *bn_inv, *bn_shift;
+};
+
+struct NfParams {
+  const uint8_t* x;
+  float* y;
+  int n, nconv;
+  int img_bytes, raw_off, raw_stride;
+  int feat_off, feat_stride, fin;
+  int dw_off, units;
+  int cst_off;
+  int zero_off, zero_bytes;
+  int bar_off;
+  const int8_t* dense_w;
+  Epi dense_epi;
+  NfLayer L[NF_MAXL];
+};
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, int* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep8x2(int (&a)[8], int (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+               :
+               : "memory");
+}
+
+// level byte of one accumulator: the fixed pipeline in its pre-scaled form (common.cuh make_qconst<false> / qaffine)
+__device__ __forceinline__ int nf_level(int acc, const QConst& q, float qm, bool sign) {
+  const float zq = qaffine<false>(acc, q);
+  if (sign) return act_sign(zq) ? 1 : -1;          // qm == 1 for sign layers: zq == z
+  return quant_scaled(zq, qm);
+}
+
+__global__ void __launch_bounds__(NF_THREADS, 1)
+vgg_fused_kernel(const __grid_constant__ NfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = (int)gridDim.x;
+  const uint32_t bar_base = smem_base + p.bar_off;
+  const uint32_t b_imfull = bar_base, b_imfree = bar_base + 8;
+  auto tfull = [&](int b) { return bar_base + 16u + 8u * b; };
+  auto tempty = [&](int b) { return bar_base + 32u + 8u * b; };
+  auto rawfull = [&](int b) { return bar_base + 48u + 8u * b; };
+  auto featfull = [&](int b) { return bar_base + 64u + 8u * b; };
+  auto actfull = [&](int l) { return bar_base + 80u + 8u * l; };
+  const uint32_t tmem_slot = bar_base + 160u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + p.bar_off + 160);
+
+  // ------------------------------------------------------------------ prologue (independent of the previous kernel)
+  if (tid == 0) {
+    griddep_launch_dependents();
+    mbar_init(b_imfull, NF_WORKERS);
+    mbar_init(b_imfree, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), 8);
+      mbar_init(rawfull(b), 1);
+      mbar_init(featfull(b), 8);
+    }
+    for (int l = 0; l < NF_MAXL; ++l) mbar_init(actfull(l), 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // halo pixels of every raster must read as zero (SAME padding); interiors are rewritten per image
+  for (int i = tid; i < (p.zero_bytes >> 4); i += NF_THREADS)
+    *reinterpret_cast<uint4*>(sg + p.zero_off + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  // A operands: kernel rows in the K-major core-matrix layout (8-row groups 256 B apart, the two 16-byte K chunks of a
+  // group 128 B apart); rows >= cout are zero
+  {
+    const NfLayer& L0 = p.L[0];
+    for (int i = tid; i < 64 * 2; i += NF_THREADS) {
+      const int row = i >> 1, chunk = i & 1;
+      uint32_t wd[4] = {0u, 0u, 0u, 0u};
+      if (row < L0.cout) {
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          const int k = chunk * 16 + b;                 // K index = (tap * cin + channel)
+          if (k < 9 * L0.cin) {
+            const int t = k / L0.cin, ci = k - t * L0.cin;
+            const uint32_t v = (uint8_t)__ldg(L0.wpk + (row * 9 + t) * L0.cin_pad + ci);
+            wd[b >> 2] |= v << (8 * (b & 3));
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(sg + L0.a_off + (row >> 3) * 256 + chunk * 128 + (row & 7) * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  }
+  for (int l = 1; l < p.nconv; ++l) {
+    const NfLayer& Ly = p.L[l];
+    const int nhalf = Ly.cin >> 5;
+    const int items = 64 * 9 * nhalf * 2;
+    const uint4* src = reinterpret_cast<const uint4*>(Ly.wpk);
+    for (int i = tid; i < items; i += NF_THREADS) {
+      const int chunk = i & 1;
+      const int j = i >> 1;
+      const int hf = j % nhalf;
+      const int rt = j / nhalf;                          // row * 9 + tap
+      const int row = rt / 9, t = rt - row * 9;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (row < Ly.cout) v = __ldg(src + i);             // packed [cout][9][cin]: 16-byte pieces in exactly this order
+      *reinterpret_cast<uint4*>(sg + Ly.a_off + (t * nhalf + hf) * NF_ABLK + (row >> 3) * 256 + chunk * 128 + (row & 7) * 16) = v;
+    }
+  }
+  for (int i = tid; i < ((p.units * p.fin) >> 4); i += NF_THREADS)
+    *reinterpret_cast<uint4*>(sg + p.dw_off + i * 16) = __ldg(reinterpret_cast<const uint4*>(p.dense_w) + i);
+  for (int i = tid; i < p.nconv * 64; i += NF_THREADS) {
+    const int l = i >> 6, c = i & 63;
+    const NfLayer& Ly = p.L[l];
+    float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < Ly.cout) {
+      const float bias = Ly.bias ? __ldg(Ly.bias + c) : 0.f;
+      const float inv = Ly.bn_inv ? __ldg(Ly.bn_inv + c) : 1.f;
+      const float shift = Ly.bn_inv ? __ldg(Ly.bn_shift + c) : 0.f;
+      k = make_float4(Ly.acc_scale, bias, __fmul_rn(inv, Ly.qm), __fmul_rn(shift, Ly.qm));
+    }
+    *reinterpret_cast<float4*>(sg + p.cst_off + i * 16) = k;
+  }
+  fence_proxy_async();                   // A blocks / zero fills were written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  griddep_wait();                        // the images / the output buffer only after the previous kernel has completed
+
+  const int nloc = p.n > (int)blockIdx.x ? (p.n - (int)blockIdx.x + G - 1) / G : 0;     // images of this CTA
+
+  if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      uint32_t q = 0;
+      for (int k = 0; k < nloc; ++k) {
+        for (int l = 0; l < p.nconv; ++l) {
+          const NfLayer& Ly = p.L[l];
+          if (l == 0) mbar_wait(b_imfull, (uint32_t)k & 1u);
+          else mbar_wait(actfull(l - 1), (uint32_t)k & 1u);
+          tc_fence_after();
+          const int nhalf = Ly.cin >> 5;
+          for (int blk = 0; blk < Ly.nblk; ++blk, ++q) {
+            const int buf = (int)(q & 1u);
+            mbar_wait(tempty(buf), ((q >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const int h0 = blk * Ly.rb;
+            const int rows = min(Ly.rb, Ly.h - h0);
+            const int N = (rows * Ly.wp + 15) & ~15;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+            if (l == 0) {
+              const uint32_t idesc = make_idesc_i8(128, N, /*a signed*/ true, /*b unsigned*/ false);
+              const uint64_t a_desc = make_smem_desc_interleaved(smem_base + Ly.a_off, 128, 256);
+              const uint64_t b_desc = make_smem_desc_interleaved(smem_base + Ly.in_off + h0 * Ly.wp * 16, Ly.in_plane, 128);
+              umma_i8(d_tmem, a_desc, b_desc, idesc, 0u);
+            } else {
+              const uint32_t idesc = make_idesc_i8(128, N, true, true);
+              for (int t = 0; t < 9; ++t) {
+                const int r = t / 3, s = t - 3 * r;
+                for (int hf = 0; hf < nhalf; ++hf) {
+                  const uint64_t a_desc = make_smem_desc_interleaved(smem_base + Ly.a_off + (t * nhalf + hf) * NF_ABLK, 128, 256);
+                  const uint64_t b_desc = make_smem_desc_interleaved(
+                      smem_base + Ly.in_off + hf * 2 * Ly.in_plane + ((h0 + r) * Ly.wp + s) * 16, Ly.in_plane, 128);
+                  umma_i8(d_tmem, a_desc, b_desc, idesc, (t | hf) ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit(tfull(buf));
+          }
+          if (l == 0) umma_commit(b_imfree);       // the im2col tile may be rebuilt once these MMAs have completed
+        }
+      }
+    }
+  } else if ((warp & 3) < 2) {
+    // ===================== epilogue (8 warps: TMEM lanes 0..63 = kernel rows) =====================
+    const int pair = warp >> 2;                    // 0..3: takes row pairs (rows) pair, pair + 4, ... of a block
+    const int half = warp & 3;                     // lanes 32 * half ..
+    const int c = half * 32 + lane;
+    uint32_t q = 0;
+    for (int k = 0; k < nloc; ++k) {
+      for (int l = 0; l < p.nconv; ++l) {
+        const NfLayer& Ly = p.L[l];
+        const bool active = half * 32 < Ly.cout;   // warp-uniform
+        const float4 kc = *reinterpret_cast<const float4*>(sg + p.cst_off + (l * 64 + c) * 16);
+        QConst qc;
+        qc.s = kc.x; qc.a = kc.y; qc.b = kc.z; qc.c = kc.w;
+        const bool dec = kc.z < 0.f;
+        const bool sign = Ly.sign != 0;
+        const float qm = Ly.qm;
+        const bool flat = Ly.out_plane == 0;
+        const int ow = Ly.pool ? (Ly.w >> 1) : Ly.w;
+        uint8_t* obase;
+        if (flat) obase = sg + p.feat_off + (k & 1) * p.feat_stride + c;
+        else obase = sg + Ly.out_off + (c >> 4) * Ly.out_plane + (c & 15);
+        for (int blk = 0; blk < Ly.nblk; ++blk, ++q) {
+          const int buf = (int)(q & 1u);
+          mbar_wait_parked(tfull(buf), (q >> 1) & 1u);
+          tc_fence_after();
+          const int h0 = blk * Ly.rb;
+          const int rows = min(Ly.rb, Ly.h - h0);
+          const uint32_t taddr = tmem_base + ((uint32_t)(half * 32) << 16) + (uint32_t)(buf * 256);
+          if (active) {
+            if (Ly.pool) {
+              const int units = rows >> 1;
+              for (int u = pair; u < units; u += 4) {
+                const int ph = (h0 >> 1) + u;
+                const uint32_t ta = taddr + (uint32_t)(2 * u * Ly.wp);
+                for (int cw = 0; cw < Ly.w; cw += 8) {
+                  int a[8], b[8];
+                  __syncwarp();
+                  tmem_ld8_nowait(ta + cw, a);
+                  tmem_ld8_nowait(ta + Ly.wp + cw, b);
+                  tmem_ld_wait_dep8x2(a, b);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int m = dec ? min(min(a[2 * i], a[2 * i + 1]), min(b[2 * i], b[2 * i + 1]))
+                                      : max(max(a[2 * i], a[2 * i + 1]), max(b[2 * i], b[2 * i + 1]));
+                    const int lv = nf_level(m, qc, qm, sign);
+                    const int pw = (cw >> 1) + i;
+                    if (pw < ow) {
+                      if (flat) obase[(ph * ow + pw) * Ly.cout] = (uint8_t)lv;
+                      else obase[((ph + 1) * Ly.out_wp + pw + 1) << 4] = (uint8_t)lv;
+                    }
+                  }
+                }
+              }
+            } else {
+              for (int u = pair; u < rows; u += 4) {
+                const int oh = h0 + u;
+                const uint32_t ta = taddr + (uint32_t)(u * Ly.wp);
+                for (int cw = 0; cw < Ly.w; cw += 16) {
+                  int a[8], b[8];
+                  __syncwarp();
+                  tmem_ld8_nowait(ta + cw, a);
+                  tmem_ld8_nowait(ta + cw + 8, b);
+                  tmem_ld_wait_dep8x2(a, b);
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int lv = nf_level(i < 8 ? a[i & 7] : b[i & 7], qc, qm, sign);
+                    const int pw = cw + i;
+                    if (pw < ow) {
+                      if (flat) obase[(oh * ow + pw) * Ly.cout] = (uint8_t)lv;
+                      else obase[((oh + 1) * Ly.out_wp + pw + 1) << 4] = (uint8_t)lv;
+                    }
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));
+        }
+        // this warp's part of the layer output is in shared memory: visible to the tensor core (async proxy) / the dense warps
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(l + 1 < p.nconv ? actfull(l) : featfull(k & 1));
+      }
+    }
+  } else {
+    // ===================== workers: image fetch, first-layer im2col, dense head =====================
+    const int wi = (warp >> 2) * 2 + (warp & 3) - 3;          // 0..6
+    const int wt = wi * 32 + lane;
+    const NfLayer& L0 = p.L[0];
+    auto fetch = [&](int k) {
+      if (k >= nloc) return;
+      const long long img = (long long)blockIdx.x + (long long)k * G;
+      mbar_expect_tx(rawfull(k & 1), (uint32_t)p.img_bytes);
+      bulk_load_1d(smem_base + p.raw_off + (k & 1) * p.raw_stride, p.x + img * p.img_bytes, (uint32_t)p.img_bytes, rawfull(k & 1));
+    };
+    ChanConst dc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dc[j] = load_chan(p.dense_epi, wi + j * NF_WORKERS, wi + j * NF_WORKERS < p.units);
+    auto dense = [&](int kk) {
+      mbar_wait_parked(featfull(kk & 1), (uint32_t)(kk >> 1) & 1u);
+      const long long img = (long long)blockIdx.x + (long long)kk * G;
+      const int* fw = reinterpret_cast<const int*>(sg + p.feat_off + (kk & 1) * p.feat_stride);
+      const int nw = p.fin >> 2;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int u = wi + j * NF_WORKERS;
+        if (u < p.units) {                                    // warp-uniform
+          const int* ww = reinterpret_cast<const int*>(sg + p.dw_off + u * p.fin);
+          int acc = 0;
+          for (int i = lane; i < nw; i += 32) acc = __dp4a(fw[i], ww[i], acc);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (lane == 0) p.y[img * p.units + u] = affine((float)acc, dc[j]);
+        }
+      }
+    };
+    if (wt == 0) fetch(0);
+    const int npix = L0.h * L0.w;
+    const int kbytes = 9 * L0.cin;
+    for (int k = 0; k < nloc; ++k) {
+      named_bar_sync(1, NF_WORKERS * 32);                     // every worker is done with raw buffer (k + 1) & 1
+      if (wt == 0) fetch(k + 1);
+      mbar_wait_parked(rawfull(k & 1), (uint32_t)(k >> 1) & 1u);
+      if (k >= 1) mbar_wait_parked(b_imfree, (uint32_t)(k - 1) & 1u);
+      const uint8_t* raw = sg + p.raw_off + (k & 1) * p.raw_stride;
+      for (int n = wt; n < npix; n += NF_WORKERS * 32) {
+        const int h = n / L0.w, w = n - h * L0.w;
+        uint32_t wd[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        int kk = 0;
+        for (int r = 0; r < 3; ++r) {
+          const int ih = h + r - 1;
+          for (int s = 0; s < 3; ++s) {
+            const int iw = w + s - 1;
+            const bool ok = ih >= 0 && ih < L0.h && iw >= 0 && iw < L0.w;
+            const uint8_t* src = raw + (ih * L0.w + iw) * L0.cin;
+            for (int ci = 0; ci < L0.cin; ++ci, ++kk) {
+              const uint32_t v = ok ? src[ci] : 0u;
+              wd[kk >> 2] |= v << (8 * (kk & 3));
+            }
+          }
+        }
+        *reinterpret_cast<uint4*>(sg + L0.in_off + n * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        if (kbytes > 16) *reinterpret_cast<uint4*>(sg + L0.in_off + L0.in_plane + n * 16) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+      }
+      fence_proxy_async();                                    // im2col rows -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_imfull);
+      if (k >= 1) dense(k - 1);
+    }
+    if (nloc >= 1) dense(nloc - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// host-side geometry; returns a message when the net is outside the kernel's scope
+const char* nf_plan(const qnnb_vgg_desc& d, NfParams& p, int& smem_bytes) {
+  memset(&p, 0, sizeof(p));
+  if (d.nconv < 1 || d.nconv > NF_MAXL) return "1..6 convolutions";
+  if (d.h < 4 || d.w < 4 || d.h > 32 || d.w > 32 || (d.cin != 1 && d.cin != 3)) return "images up to 32x32 with 1 or 3 channels";
+  if (d.units < 1 || d.units > 3 * NF_WORKERS) return "at most 21 dense units";
+  if ((d.h * d.w * d.cin) % 16 != 0) return "image bytes must be a multiple of 16";
+  int off = 0;
+  // A blocks
+  int h = d.h, w = d.w, cin = d.cin;
+  for (int l = 0; l < d.nconv; ++l) {
+    const qnnb_net_conv& c = d.conv[l];
+    NfLayer& L = p.L[l];
+    if (c.cout != 32 && c.cout != 64) return "32 or 64 filters per layer";
+    if (c.epi.act != QNNB_ACT_QUANT && c.epi.act != QNNB_ACT_SIGN_I8) return "quantized_tanh / binary_tanh (int8 levels) activations";
+    if (c.epi.res_kind != QNNB_KIND_NONE) return "no residual";
+    if (c.pool != 0 && c.pool != 2) return "pool 0 or 2";
+    if (c.pool && (h < 2 || w < 2)) return "pooled map would be empty";
+    if (!c.w) return "null kernel";
+    L.h = h; L.w = w; L.cin = cin; L.cout = c.cout;
+    L.pool = c.pool ? 1 : 0;
+    L.sign = c.epi.act == QNNB_ACT_SIGN_I8;
+    L.qm = L.sign ? 1.f : (float)(1 << (c.epi.abits - 1));
+    L.acc_scale = c.epi.acc_scale;
+    L.wpk = (const int8_t*)c.w; L.bias = c.epi.bias; L.bn_inv = c.epi.bn_inv; L.bn_shift = c.epi.bn_shift;
+    L.cin_pad = (cin + 3) & ~3;
+    L.wp = l == 0 ? w : w + 2;
+    L.a_off = off;
+    off += (l == 0 ? 1 : 9 * (cin / 32)) * NF_ABLK;
+    // rows per block: N = rows * pitch (+ the 8-column loads' overhang past the last row) <= 256 accumulator columns
+    const int step = L.pool ? 8 : 16;
+    const int over = ((w + step - 1) / step) * step - L.wp;
+    const int limit = 256 - (over > 0 ? over : 0);
+    int rb = limit / L.wp;
+    if (L.pool) rb &= ~1;
+    if (rb < (L.pool ? 2 : 1)) return "map too wide";
+    if (rb > h) rb = h;
+    int nblk = (h + rb - 1) / rb;
+    if (nblk == 1 && h >= 8) nblk = 2;                 // two blocks: the second block's MMAs overlap the first one's epilogue
+    rb = (h + nblk - 1) / nblk;
+    if (L.pool) rb = (rb + 1) & ~1;
+    nblk = (h + rb - 1) / rb;
+    L.rb = rb; L.nblk = nblk;
+    if (L.pool) { h >>= 1; w >>= 1; }
+    cin = c.cout;
+  }
+  off += NF_ABLK;                                       // the last block's rows 64..127 are read from here
+  const int fin = h * w * cin;
+  if (h < 1 || w < 1) return "empty feature map";
+  if (!d.dense_w) return "null dense kernel";
+  // first-layer im2col: two 16-byte K planes of (pixels + 16) rows
+  {
+    NfLayer& L = p.L[0];
+    L.in_off = off;
+    L.in_plane = (L.h * L.w + 16) * 16;
+    off += 2 * L.in_plane;
+  }
+  // rasters (inputs of layers 1..): zero-haloed maps, cin / 16 planes
+  p.zero_off = off;
+  for (int l = 1; l < d.nconv; ++l) {
+    NfLayer& L = p.L[l];
+    L.in_off = off;
+    L.in_plane = ((L.h + 3) * L.wp + 32) * 16;
+    off += (L.cin / 16) * L.in_plane;
+    p.L[l - 1].out_off = L.in_off; p.L[l - 1].out_plane = L.in_plane; p.L[l - 1].out_wp = L.wp;
+  }
+  p.zero_bytes = off - p.zero_off;
+  p.L[d.nconv - 1].out_plane = 0;
+  p.fin = fin;
+  p.feat_stride = (fin + 15) & ~15;
+  p.feat_off = off; off += 2 * p.feat_stride;
+  p.dw_off = off; off += (d.units * fin + 15) & ~15;
+  p.img_bytes = d.h * d.w * d.cin;
+  p.raw_stride = p.img_bytes;
+  p.raw_off = off; off += 2 * p.raw_stride;
+  p.cst_off = off; off += d.nconv * 64 * 16;
+  p.bar_off = (off + 15) & ~15; off = p.bar_off + 256;
+  smem_bytes = off + 1024;
+  if (smem_bytes > NF_SMEM_MAX) return "kernels + activation maps exceed one SM's shared memory";
+  p.n = d.n; p.nconv = d.nconv; p.units = d.units;
+  p.dense_w = (const int8_t*)d.dense_w;
+  p.dense_epi = make_epi(d.dense_epi);
+  return nullptr;
+}
+
+}  // namespace
+
+bool vgg_fused_supported(const qnnb_vgg_desc& d, const char** why) {
+  NfParams p;
+  int smem = 0;
+  const char* msg = nf_plan(d, p, smem);
+  if (why) *why = msg ? msg : "";
+  return msg == nullptr;
+}
+
+int launch_vgg_fused(const qnnb_vgg_desc& d, const void* x, float* y, cudaStream_t st) {
+  NfParams p;
+  int smem = 0;
+  const char* msg = nf_plan(d, p, smem);
+  if (msg) { set_error("vgg_forward: outside the whole-network kernel's scope (%s)", msg); return QNNB_EUNSUPPORTED; }
+  if (((uintptr_t)x & 15u) != 0) { set_error("vgg_forward: the image batch must be 16-byte aligned"); return QNNB_EINVAL; }
+  p.x = (const uint8_t*)x; p.y = y;
+  static SmemConfigured once;
+  QNNB_CUDA(once.ensure(vgg_fused_kernel, smem));
+  const int grid = d.n < sm_count() ? d.n : sm_count();
+  QNNB_CUDA(launch_pdl(vgg_fused_kernel, dim3(grid), dim3(NF_THREADS), (size_t)smem, st, p));
+  return QNNB_OK;
+}
+
+}  // namespace qnnb

@@ -183,6 +183,41 @@ def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=Fa
     return out, logits
 
 
+# --------------------------------------------------------------------------- whole-network launch
+def vgg_desc(n, h, w, cin, convs, units, dense_w, dense_epi) -> L.VggDesc:
+    """``convs``: list of (cout, pool, packed kernel, Epilogue) -- see ``qnnb_vgg_desc`` in include/qnnb200.h."""
+    d = L.VggDesc()
+    d.n, d.h, d.w, d.cin = int(n), int(h), int(w), int(cin)
+    d.nconv = len(convs)
+    if len(convs) > L.NET_MAX_CONVS:
+        raise ValueError("vgg_desc: at most %d convolutions" % L.NET_MAX_CONVS)
+    for i, (cout, pool, wp, epi) in enumerate(convs):
+        d.conv[i].cout, d.conv[i].pool = int(cout), int(pool)
+        d.conv[i].w = L.ptr(wp)
+        d.conv[i].epi = epi
+    d.units = int(units)
+    d.dense_w = L.ptr(dense_w)
+    d.dense_epi = dense_epi
+    d._refs = (convs, dense_w, dense_epi)
+    return d
+
+
+def vgg_forward_supported(d: L.VggDesc) -> bool:
+    return bool(L.lib().qnnb_vgg_forward_supported(C.byref(d)))
+
+
+def vgg_forward(d: L.VggDesc, x: torch.Tensor, out=None):
+    """One launch: uint8 images [n, h, w, cin] -> fp32 [n, units] (models/vgg.py:15-42 end to end)."""
+    if x.dtype != torch.uint8:
+        raise TypeError("vgg_forward takes uint8 pixel levels")
+    if out is None:
+        out = torch.empty((int(d.n), int(d.units)), dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (int(d.n), int(d.units)) or out.dtype != torch.float32:
+        raise ValueError("vgg_forward: bad output buffer %s/%s" % (tuple(out.shape), out.dtype))
+    L.check(L.lib().qnnb_vgg_forward(C.byref(d), L.ptr(x), L.ptr(out), L.current_stream_ptr()))
+    return out
+
+
 # --------------------------------------------------------------------------- stand-alone ops
 def quantize_act(x: torch.Tensor, abits: int) -> QTensor:
     x = x.contiguous()

@@ -10,6 +10,7 @@ kernel over the un-pooled map with the packed kernel replicated per pixel.
 from __future__ import annotations
 
 import gc
+import os
 import weakref
 
 import numpy as np
@@ -82,6 +83,9 @@ class Plan:
         self._slots = {}
         self._compile()
         self.launches_per_forward = len(self.steps)
+        # whole-network launch (csrc/net_fused.cu): decided on the first forward (needs the input shape); None = not yet
+        self.fuse = self.impl == L.IMPL_AUTO and os.environ.get("QNNB_FUSED_NET", "1") != "0"
+        self._fused_ok = {}
         self._layers = [t.layer for t in self.order]
         self._epoch = -1
         self._versions = None
@@ -348,10 +352,89 @@ class Plan:
             env[st.out] = y if isinstance(y, K.QTensor) else K.as_qtensor(y)
             self.launches += 1
 
-    def run(self, x, out=None) -> dict:
-        """One forward over a device batch.  Returns the environment (tensor index -> QTensor)."""
+    # ------------------------------------------------------------------ whole-network launch
+    def _fused_chain(self):
+        """The plan as (conv steps, dense step) when it is the plain models/vgg.py chain -- every conv 3x3 stride 1 fed by
+        the previous one, quantised / binary activation, no residual, then Flatten -> Fc [-> BN] -- else None."""
+        if len(self.steps) < 2 or self.steps[-1].kind != "dense" or any(st.kind != "conv" for st in self.steps[:-1]):
+            return None
+        if len(self.steps) - 1 > L.NET_MAX_CONVS:
+            return None
+        prev = self.input_idx
+        for st in self.steps[:-1]:
+            lay = st.layer
+            if st.src != prev or st.res is not None or st.act is None or st.act[0] not in ("quant", "binary"):
+                return None
+            if tuple(lay.kernel_size) != (3, 3) or tuple(lay.strides) != (1, 1):
+                return None
+            prev = st.out
+        dn = self.steps[-1]
+        if dn.softmax or dn.out != self.output_idx:
+            return None
+        cur, flat = dn.src, False
+        while cur in self.alias:
+            if self.alias[cur][0] != "flatten":
+                return None
+            flat, cur = True, self.alias[cur][1]
+        if cur != prev or not flat:
+            return None
+        return self.steps[:-1], dn
+
+    def _fused_desc(self, x):
+        """qnnb_vgg_desc of this plan for the uint8 batch ``x`` (QTensor), or None when the net is out of its scope."""
+        chain = self._fused_chain()
+        if chain is None or x.kind != "u8":
+            return None
+        convs, dn = chain
+        dev = x.data.device
+        n, h, w, cin = (int(v) for v in x.shape)
+        scale_in, rows = x.scale, []
+        for st in convs:
+            lay = st.layer
+            _, _, _, wscale = lay.weight_mode()
+            inv = shift = None
+            if st.bn is not None:
+                inv, shift = self._bn_dev(st, st.bn, dev)
+            if st.act[0] == "quant":
+                act, abits, scale_out = L.ACT_QUANT, int(st.act[1]), 1.0 / float(1 << (int(st.act[1]) - 1))
+            else:
+                act, abits, scale_out = L.ACT_SIGN_I8, 0, 1.0
+            epi = K.make_epilogue(K.acc_scale(scale_in, wscale), bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift,
+                                  act=act, abits=abits, pool=2 if st.pool else 0)
+            rows.append((lay.filters, 2 if st.pool else 0, lay.packed_kernel(dev, L.WFMT_I8), epi))
+            scale_in = scale_out
+            if st.pool:
+                h, w = h // 2, w // 2
+        lay = dn.layer
+        if h < 1 or w < 1 or lay.kernel.shape[0] != h * w * convs[-1].layer.filters:
+            return None
+        _, _, _, wscale = lay.weight_mode()
+        inv = shift = None
+        if dn.bn is not None:
+            inv, shift = self._bn_dev(dn, dn.bn, dev)
+        depi = K.make_epilogue(K.acc_scale(scale_in, wscale), bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift)
+        d = K.vgg_desc(n, int(x.shape[1]), int(x.shape[2]), cin, rows, lay.units, lay.packed_kernel(dev, L.WFMT_I8), depi)
+        return d if K.vgg_forward_supported(d) else None
+
+    def fused_available(self, x) -> bool:
+        """Would ``forward`` run this batch as ONE whole-network launch?"""
+        x = K.as_qtensor(x)
+        key = (x.kind,) + tuple(x.shape[1:])
+        if key not in self._fused_ok:
+            self._fused_ok[key] = self.fuse and self._fused_desc(x) is not None
+        return self._fused_ok[key]
+
+    def run(self, x, out=None, fuse=False) -> dict:
+        """One forward over a device batch.  Returns the environment (tensor index -> QTensor).  ``fuse``: take the
+        whole-network launch when the net qualifies (the environment then holds the input and the output only)."""
         self._sync_weights()
         env = {self.input_idx: K.as_qtensor(x)}
+        if fuse and int(env[self.input_idx].data.shape[0]) > 0 and self.fused_available(env[self.input_idx]):
+            d = self._fused_desc(env[self.input_idx])
+            y = K.vgg_forward(d, env[self.input_idx].data, out=out)
+            env[self.output_idx] = K.QTensor("f32", y, 1.0, int(d.units))
+            self.launches += 1
+            return env
         if out is not None:
             env["out_buffer"] = out
         for st in self.steps:
@@ -363,7 +446,7 @@ class Plan:
     def forward(self, x, return_logits=False, out=None):
         """``out``: optional [N, units] fp32 destination of the network output (a CUDA tensor or an
         ``_lib.DeviceBuffer``, e.g. ``sharding.PeerGather.block()``), written by the final dense kernel itself."""
-        env = self.run(x, out=out)
+        env = self.run(x, out=out, fuse=True)
         out = env[self.output_idx]
         out = out.data if out.kind == "f32" else out.to_float()
         if return_logits:
@@ -419,10 +502,13 @@ class Plan:
             if not ring["slots"]:
                 self.forward(x_dev)                     # packs weights / uploads constants outside the capture
                 torch.cuda.synchronize()
+            before = self.launches
             g, out_dev = self._capture(x_dev, st)
+            per_forward = self.launches - before           # 1 when the whole net is one launch
+            self.launches = before
             out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype).pin_memory()
             ring["slots"].append({"stream": st, "x": x_dev, "graph": g, "out": out_dev, "host": out_host,
-                                  "event": torch.cuda.Event(), "owner": None, "gen": 0})
+                                  "event": torch.cuda.Event(), "owner": None, "gen": 0, "launches": per_forward})
         slot = ring["slots"][ring["next"] % len(ring["slots"])] if len(ring["slots"]) == self.PIPELINE_DEPTH else ring["slots"][-1]
         ring["next"] += 1
         return slot
@@ -450,7 +536,7 @@ class Plan:
                 slot["out"].copy_(self.forward(slot["x"]))
             slot["host"].copy_(slot["out"], non_blocking=True)
             slot["event"].record(slot["stream"])
-        self.launches += self.launches_per_forward
+        self.launches += slot["launches"]
         h = _Handle(slot)
         slot["owner"] = h
         return h

@@ -59,6 +59,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(qnnb_epilogue), sizeof(qnnb_conv_desc), sizeof(qnnb_dense_desc),
          offsetof(qnnb_conv_desc, epi), offsetof(qnnb_dense_desc, epi), offsetof(qnnb_epilogue, residual),
          offsetof(qnnb_epilogue, pool), offsetof(qnnb_dense_desc, avg_positions));
+  printf("%zu %zu %zu %zu %zu %zu %d\n", sizeof(qnnb_net_conv), sizeof(qnnb_vgg_desc), offsetof(qnnb_net_conv, epi),
+         offsetof(qnnb_vgg_desc, conv), offsetof(qnnb_vgg_desc, dense_w), offsetof(qnnb_vgg_desc, dense_epi), QNNB_NET_MAX_CONVS);
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -66,7 +68,9 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), "-o", os.path.join(td, "t"), os.path.join(td, "t.c")])
         got = [int(v) for v in subprocess.check_output([os.path.join(td, "t")]).split()]
     want = [C.sizeof(L.Epilogue), C.sizeof(L.ConvDesc), C.sizeof(L.DenseDesc), L.ConvDesc.epi.offset,
-            L.DenseDesc.epi.offset, L.Epilogue.residual.offset, L.Epilogue.pool.offset, L.DenseDesc.avg_positions.offset]
+            L.DenseDesc.epi.offset, L.Epilogue.residual.offset, L.Epilogue.pool.offset, L.DenseDesc.avg_positions.offset,
+            C.sizeof(L.NetConv), C.sizeof(L.VggDesc), L.NetConv.epi.offset, L.VggDesc.conv.offset, L.VggDesc.dense_w.offset,
+            L.VggDesc.dense_epi.offset, L.NET_MAX_CONVS]
     assert got == want
 
 
@@ -165,3 +169,44 @@ def test_dense_rejects_pooled_integer_input_without_a_gpu():
     d.avg_positions = 64
     rc = h.qnnb_dense(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), C.c_void_p(0x1000), None, None)
     assert rc == L.EINVAL and b"avg_positions" in h.qnnb_last_error()
+
+
+def _vgg_desc(h, w, cin, filters, pools, abits=2, units=10, n=100):
+    d = L.VggDesc()
+    d.n, d.h, d.w, d.cin, d.nconv, d.units = n, h, w, cin, len(filters), units
+    for i, (f, pl) in enumerate(zip(filters, pools)):
+        d.conv[i].cout, d.conv[i].pool, d.conv[i].w = f, pl, 0x1000
+        d.conv[i].epi.acc_scale = 1.0
+        d.conv[i].epi.res_kind = L.KIND_NONE
+        d.conv[i].epi.act, d.conv[i].epi.abits = L.ACT_QUANT, abits
+    d.dense_w = 0x1000
+    d.dense_epi.acc_scale = 1.0
+    d.dense_epi.res_kind = L.KIND_NONE
+    return d
+
+
+def test_whole_network_scope_query_is_pure_host_logic():
+    """qnnb_vgg_forward_supported: which nets run as ONE launch (csrc/net_fused.cu) -- BASELINE config 1 and the
+    64/64/64 CIFAR-10 variant do, the headline 64/128/256 net (288 KB of kernels in the last conv) does not."""
+    h = L.lib()
+    q = lambda d: h.qnnb_vgg_forward_supported(C.byref(d))
+    assert q(_vgg_desc(28, 28, 1, [64, 64, 64], [2, 2, 2])) == 1                    # cfg1
+    assert q(_vgg_desc(32, 32, 3, [64, 64, 64], [2, 2, 2], abits=4)) == 1           # config/config_CIFAR-10.py
+    assert q(_vgg_desc(32, 32, 3, [32, 64, 32], [2, 2, 2], abits=8)) == 1
+    assert q(_vgg_desc(28, 28, 1, [32, 32, 64, 64], [0, 2, 2, 2])) == 1             # nla = 2: an un-pooled 28x28 layer
+    assert q(_vgg_desc(32, 32, 3, [64, 64, 64, 64], [2, 0, 2, 2], abits=4)) == 1    # nlb = 2
+    assert q(_vgg_desc(32, 32, 3, [64, 128, 256], [2, 2, 2], abits=4)) == 0         # cfg3
+    assert q(_vgg_desc(32, 32, 3, [64, 64, 64, 64, 64, 64], [0, 0, 2, 0, 2, 2])) == 0   # maps + kernels > 227 KB
+    assert q(_vgg_desc(64, 64, 3, [64, 64, 64], [2, 2, 2])) == 0
+    assert q(_vgg_desc(28, 28, 1, [64, 64, 64], [2, 2, 2], units=40)) == 0
+    d = _vgg_desc(28, 28, 1, [64, 64, 64], [2, 2, 2])
+    d.conv[1].epi.act = L.ACT_LEAKY
+    assert q(d) == 0
+    assert h.qnnb_vgg_forward_supported(None) == 0
+    # argument errors surface as status codes
+    d = _vgg_desc(28, 28, 1, [64, 64, 64], [2, 2, 2])
+    d.nconv = 9
+    assert h.qnnb_vgg_forward(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), None) == L.EINVAL
+    d = _vgg_desc(32, 32, 3, [64, 128, 256], [2, 2, 2], abits=4)
+    assert h.qnnb_vgg_forward(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), None) == L.EUNSUPPORTED
+    assert b"whole-network" in h.qnnb_last_error()
