@@ -480,16 +480,28 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     # ---- per-kernel timing (CUDA events around a graph of REPS launches, same rotating inputs) for the roofline
     envs = [plan.run(bufs[i]) for i in range(2)]
     work = plan_work(plan, envs[0])
-    per = np.zeros(len(plan.steps))
+    fused = plan.fused_available(bufs[0])
+    timed_steps = list(plan.steps)
+    if fused:
+        # the whole net is ONE launch (csrc/net_fused.cu): one row -- ops of every layer; bytes = what crosses HBM, i.e. the
+        # images in, the logits out and the packed kernels once
+        kern_bytes = sum(float(st.layer.kernel.size) for st in plan.steps)
+        work = [("net (whole-network kernel)", float(sum(w[1] for w in work)), float(batch * (img_bytes + cf.classes * 4) + kern_bytes),
+                 ("net", cf.dim, cf.channels, tuple(st.layer.kernel.shape[-1] for st in plan.steps)))]
+        timed_steps = [None]
+    per = np.zeros(len(timed_steps))
     REPS = 10
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
-    for si, st in enumerate(plan.steps):
+    for si, st in enumerate(timed_steps):
         g = torch.cuda.CUDAGraph()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
                 for r in range(REPS):
+                    if st is None:
+                        plan.forward(bufs[r % 2])
+                        continue
                     env = dict(envs[r % 2])
                     plan.run_step(st, env)
         torch.cuda.current_stream().wait_stream(side)
@@ -520,7 +532,7 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     r0 = rows[members[0]]
     achieved = (ops / (kernel_ms * 1e-3) / 1e12) if r0["bound"] == "tensor" else (byts / (kernel_ms * 1e-3) / 1e9)
     roof = {"bound": r0["bound"], "achieved": achieved, "peak": r0["peak"], "unit": r0["unit"], "frac": achieved / r0["peak"],
-            "traffic": ncu_traffic(name, members, len(plan.steps)), "kernel": kname, "kernel_ms": kernel_ms,
+            "traffic": None if fused else ncu_traffic(name, members, len(plan.steps)), "kernel": kname, "kernel_ms": kernel_ms,
             "peak_source": i8_src if r0["bound"] == "tensor" else pk["source"] + " copy bandwidth",
             "share_of_step": float(sum(per[i] for i in members) / max(per.sum(), 1e-30)),
             "algorithmic": {"ops_per_launch": float(ops), "bytes_per_launch": float(byts)},

@@ -181,8 +181,12 @@ int qnnb_dequantize(int32_t kind, const void* x, int64_t count, int32_t channels
  * (conv -> BatchNormalization -> Activation [-> MaxPooling2D]) x nconv, Flatten, Fc, BatchNormalization -- in ONE
  * kernel; an image stays in one SM's shared memory from the input bytes to the logits (csrc/net_fused.cu).  Covers
  * nets whose packed kernels and activation maps fit there: images up to 32x32 with 1 or 3 channels, 3x3 stride-1
- * convolutions with 32 or 64 filters, quantized_tanh / binary_tanh activations kept as int8 levels, <= 21 units.
- * Same arithmetic as the per-layer entry points (bit-identical results).
+ * convolutions with 32 or 64 filters, quantized_tanh / binary_tanh activations kept as int8 levels, <= 32 units.
+ * Same arithmetic as the per-layer entry points (bit-identical results).  Two steps, like qnnb_pack_weights + qnnb_conv2d:
+ * qnnb_vgg_pack builds the net's resident image once per set of weights -- every layer's kernel in tensor-core operand
+ * order, the dense kernel, the per-channel epilogue constants, qnnb_vgg_blob_bytes(desc) bytes of device memory -- and
+ * qnnb_vgg_forward (same descriptor; its weight / bias / BN pointers are not read again) brings it into each SM with
+ * bulk copies and runs the batch.
  *   conv[l].w   : packed by qnnb_pack_weights (QNNB_WFMT_I8), cin = image channels (l = 0) or conv[l-1].cout
  *   conv[l].epi : acc_scale, bias, bn_inv / bn_shift, act (QNNB_ACT_QUANT + abits | QNNB_ACT_SIGN_I8); `pool` of the
  *                 epilogue is ignored in favour of conv[l].pool
@@ -208,7 +212,9 @@ typedef struct qnnb_vgg_desc {
 
 /* 1 when qnnb_vgg_forward covers this net, else 0 (the host then runs the per-layer plan) */
 int qnnb_vgg_forward_supported(const qnnb_vgg_desc* desc);
-int qnnb_vgg_forward(const qnnb_vgg_desc* desc, const void* x, float* y, void* stream);
+int64_t qnnb_vgg_blob_bytes(const qnnb_vgg_desc* desc);          /* 0 when the net is not covered */
+int qnnb_vgg_pack(const qnnb_vgg_desc* desc, void* blob, void* stream);
+int qnnb_vgg_forward(const qnnb_vgg_desc* desc, const void* blob, const void* x, float* y, void* stream);
 
 /*
  * NVLink logit path for batch-sharded inference (one process per GPU of one box): the reference evaluates a test set

@@ -91,7 +91,9 @@ PROTOTYPES = {
     "qnnb_conv2d_out_shape": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qnnb_dense": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_vgg_forward_supported": (C.c_int, [C.POINTER(VggDesc)]),
-    "qnnb_vgg_forward": (C.c_int, [C.POINTER(VggDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qnnb_vgg_blob_bytes": (C.c_int64, [C.POINTER(VggDesc)]),
+    "qnnb_vgg_pack": (C.c_int, [C.POINTER(VggDesc), C.c_void_p, C.c_void_p]),
+    "qnnb_vgg_forward": (C.c_int, [C.POINTER(VggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_quantize_act": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "qnnb_batchnorm_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qnnb_maxpool2_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

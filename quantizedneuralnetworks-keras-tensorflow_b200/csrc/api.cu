@@ -156,20 +156,39 @@ int qnnb_vgg_forward_supported(const qnnb_vgg_desc* d) {
   return vgg_fused_supported(*d, &why) ? 1 : 0;
 }
 
-int qnnb_vgg_forward(const qnnb_vgg_desc* d, const void* x, float* y, void* stream) {
-  QNNB_CHECK_ARG(d, "vgg_forward: null descriptor");
-  QNNB_CHECK_ARG(d->n >= 0, "vgg_forward: bad batch size %d", d->n);
-  QNNB_CHECK_ARG(d->nconv >= 1 && d->nconv <= QNNB_NET_MAX_CONVS, "vgg_forward: nconv=%d outside 1..%d", d->nconv, QNNB_NET_MAX_CONVS);
+static int validate_vgg(const qnnb_vgg_desc* d, const char* who) {
+  QNNB_CHECK_ARG(d, "%s: null descriptor", who);
+  QNNB_CHECK_ARG(d->n >= 0, "%s: bad batch size %d", who, d->n);
+  QNNB_CHECK_ARG(d->nconv >= 1 && d->nconv <= QNNB_NET_MAX_CONVS, "%s: nconv=%d outside 1..%d", who, d->nconv, QNNB_NET_MAX_CONVS);
   for (int l = 0; l < d->nconv; ++l) {
     int rc = validate_epilogue(d->conv[l].epi, true, false);
     if (rc) return rc;
   }
   int rc = validate_epilogue(d->dense_epi, false, false);
   if (rc) return rc;
-  QNNB_CHECK_ARG(d->dense_epi.act == QNNB_ACT_NONE, "vgg_forward: the dense head has no activation (act=%d)", d->dense_epi.act);
+  QNNB_CHECK_ARG(d->dense_epi.act == QNNB_ACT_NONE, "%s: the dense head has no activation (act=%d)", who, d->dense_epi.act);
+  return QNNB_OK;
+}
+
+int64_t qnnb_vgg_blob_bytes(const qnnb_vgg_desc* d) {
+  if (!d || validate_vgg(d, "vgg_blob_bytes") != QNNB_OK) return 0;
+  return (int64_t)vgg_fused_blob_bytes(*d);
+}
+
+int qnnb_vgg_pack(const qnnb_vgg_desc* d, void* blob, void* stream) {
+  int rc = validate_vgg(d, "vgg_pack");
+  if (rc) return rc;
+  return launch_vgg_pack(*d, blob, (cudaStream_t)stream);
+}
+
+int qnnb_vgg_forward(const qnnb_vgg_desc* d, const void* blob, const void* x, float* y, void* stream) {
+  int rc = validate_vgg(d, "vgg_forward");
+  if (rc) return rc;
+  const char* why = "";
+  if (!vgg_fused_supported(*d, &why)) { set_error("vgg_forward: outside the whole-network kernel's scope (%s)", why); return QNNB_EUNSUPPORTED; }
   if (d->n == 0) return QNNB_OK;
-  QNNB_CHECK_ARG(x && y, "vgg_forward: null pointer");
-  return launch_vgg_fused(*d, x, y, (cudaStream_t)stream);
+  QNNB_CHECK_ARG(blob && x && y, "vgg_forward: null pointer");
+  return launch_vgg_fused(*d, blob, x, y, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -211,7 +211,9 @@ int launch_conv_f32_tc(const qnnb_conv_desc& d, const void* x, const void* w, vo
 void set_trace_buffer(unsigned long long* buf, int cap);
 unsigned long long* get_trace_buffer();
 bool vgg_fused_supported(const qnnb_vgg_desc& d, const char** why);
-int launch_vgg_fused(const qnnb_vgg_desc& d, const void* x, float* y, cudaStream_t st);
+long long vgg_fused_blob_bytes(const qnnb_vgg_desc& d);
+int launch_vgg_pack(const qnnb_vgg_desc& d, void* blob, cudaStream_t st);
+int launch_vgg_fused(const qnnb_vgg_desc& d, const void* blob, const void* x, float* y, cudaStream_t st);
 int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* y, float* logits, cudaStream_t st);
 
 }  // namespace qnnb

@@ -206,7 +206,18 @@ def vgg_forward_supported(d: L.VggDesc) -> bool:
     return bool(L.lib().qnnb_vgg_forward_supported(C.byref(d)))
 
 
-def vgg_forward(d: L.VggDesc, x: torch.Tensor, out=None):
+def vgg_pack(d: L.VggDesc, device) -> torch.Tensor:
+    """The net's resident image (kernels in tensor-core operand order + dense kernel + epilogue constants): build once
+    per set of weights, pass to every ``vgg_forward``."""
+    nbytes = int(L.lib().qnnb_vgg_blob_bytes(C.byref(d)))
+    if nbytes <= 0:
+        raise ValueError("vgg_pack: this net is outside the whole-network kernel's scope")
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    L.check(L.lib().qnnb_vgg_pack(C.byref(d), L.ptr(blob), L.current_stream_ptr()))
+    return blob
+
+
+def vgg_forward(d: L.VggDesc, blob: torch.Tensor, x: torch.Tensor, out=None):
     """One launch: uint8 images [n, h, w, cin] -> fp32 [n, units] (models/vgg.py:15-42 end to end)."""
     if x.dtype != torch.uint8:
         raise TypeError("vgg_forward takes uint8 pixel levels")
@@ -214,7 +225,7 @@ def vgg_forward(d: L.VggDesc, x: torch.Tensor, out=None):
         out = torch.empty((int(d.n), int(d.units)), dtype=torch.float32, device=x.device)
     elif tuple(out.shape) != (int(d.n), int(d.units)) or out.dtype != torch.float32:
         raise ValueError("vgg_forward: bad output buffer %s/%s" % (tuple(out.shape), out.dtype))
-    L.check(L.lib().qnnb_vgg_forward(C.byref(d), L.ptr(x), L.ptr(out), L.current_stream_ptr()))
+    L.check(L.lib().qnnb_vgg_forward(C.byref(d), L.ptr(blob), L.ptr(x), L.ptr(out), L.current_stream_ptr()))
     return out
 
 

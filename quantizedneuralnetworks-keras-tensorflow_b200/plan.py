@@ -430,8 +430,15 @@ class Plan:
         self._sync_weights()
         env = {self.input_idx: K.as_qtensor(x)}
         if fuse and int(env[self.input_idx].data.shape[0]) > 0 and self.fused_available(env[self.input_idx]):
-            d = self._fused_desc(env[self.input_idx])
-            y = K.vgg_forward(d, env[self.input_idx].data, out=out)
+            xq = env[self.input_idx]
+            d = self._fused_desc(xq)
+            # the resident image depends on the weights and the map geometry, not on the batch: cached with the other
+            # per-step device constants (dropped by close() when a layer's weights change)
+            key = ("vggblob", str(xq.data.device)) + tuple(xq.shape[1:])
+            dev0 = self.steps[0].dev
+            if key not in dev0:
+                dev0[key] = K.vgg_pack(d, xq.data.device)
+            y = K.vgg_forward(d, dev0[key], xq.data, out=out)
             env[self.output_idx] = K.QTensor("f32", y, 1.0, int(d.units))
             self.launches += 1
             return env

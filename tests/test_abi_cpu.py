@@ -206,7 +206,11 @@ def test_whole_network_scope_query_is_pure_host_logic():
     # argument errors surface as status codes
     d = _vgg_desc(28, 28, 1, [64, 64, 64], [2, 2, 2])
     d.nconv = 9
-    assert h.qnnb_vgg_forward(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), None) == L.EINVAL
+    assert h.qnnb_vgg_forward(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), C.c_void_p(0x1000), None) == L.EINVAL
     d = _vgg_desc(32, 32, 3, [64, 128, 256], [2, 2, 2], abits=4)
-    assert h.qnnb_vgg_forward(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), None) == L.EUNSUPPORTED
+    assert h.qnnb_vgg_forward(C.byref(d), C.c_void_p(0x1000), C.c_void_p(0x1000), C.c_void_p(0x1000), None) == L.EUNSUPPORTED
     assert b"whole-network" in h.qnnb_last_error()
+    assert h.qnnb_vgg_blob_bytes(C.byref(d)) == 0
+    # resident image of cfg1: (1 + 18 + 18 + 1) A blocks of 2 KB, the 10 x 576 dense kernel, 3 x 64 + 10 constant rows
+    d = _vgg_desc(28, 28, 1, [64, 64, 64], [2, 2, 2])
+    assert h.qnnb_vgg_blob_bytes(C.byref(d)) == 38 * 2048 + 5760 + 192 * 16 + 160
