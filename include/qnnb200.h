@@ -46,10 +46,12 @@ extern "C" {
 #define QNNB_W_QUANT    0      /* quantize(W, nb)   layers/quantized_ops.py:49-66 */
 #define QNNB_W_BINARY   1      /* binarize(W, H)    layers/binary_ops.py:54-64    */
 #define QNNB_W_TERNARY  2      /* ternarize(W, H)   layers/ternary_ops.py:15-41   */
+#define QNNB_W_FLOAT    3      /* no quantiser: the plain Conv2D / Dense of network_type 'float' (models/model_factory.py:24-27) */
 
 /* packed weight formats */
 #define QNNB_WFMT_I8    0      /* int8 levels  [cout][kh][kw][cin_pad], cin_pad = cin rounded up to 4, zero filled */
 #define QNNB_WFMT_B1    1      /* uint32 words [cout][kh][kw][ceil(cin/32)], pad bits zero */
+#define QNNB_WFMT_F32   2      /* float        [cout][kh][kw][cin_pad] (QNNB_W_FLOAT only; consumed with in_kind F32 and w_f32 = 1) */
 
 /* fused activation */
 #define QNNB_ACT_NONE   0      /* fp32 out */
@@ -98,6 +100,7 @@ typedef struct qnnb_conv_desc {
   int32_t in_kind;          /* QNNB_KIND_U8 | I8 | B1 | F32 */
   int32_t impl;             /* QNNB_IMPL_* */
   qnnb_epilogue epi;
+  int32_t w_f32;            /* 1: `w` is a QNNB_WFMT_F32 kernel (fp32 values, 'float' networks); needs in_kind F32.  0: levels */
 } qnnb_conv_desc;
 
 /* Dense layer  y[n][u] = epilogue( sum_f x[n][f] * w[u][f] ), optional softmax. */
@@ -109,6 +112,7 @@ typedef struct qnnb_dense_desc {
   int32_t avg_positions;    /* 0 | 1: plain.  P > 1 (fp32 input only): x is [n][P][fin] and the layer sees the SUM over the P
                                positions -- AveragePooling2D(8) + Flatten of models/resnet.py:134-135 folded in; acc_scale
                                carries the 1/P */
+  int32_t w_f32;            /* 1: `w` is a QNNB_WFMT_F32 kernel; needs in_kind F32 */
 } qnnb_dense_desc;
 
 int         qnnb_version(void);
@@ -121,7 +125,8 @@ int         qnnb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_m
  * binarize / ternarize on every forward: quantized_layers.py:80,165; binary_layers.py:79,161;
  * ternary_layers.py:78,157).
  *   w_hwio : fp32 (kh,kw,cin,cout) -- Keras HWIO; a Dense kernel (in,units) is kh=kw=1.
- *   out    : QNNB_WFMT_I8 -> int8  [cout][kh][kw][cin_pad]; QNNB_WFMT_B1 -> uint32 [cout][kh][kw][ceil(cin/32)]
+ *   out    : QNNB_WFMT_I8 -> int8  [cout][kh][kw][cin_pad]; QNNB_WFMT_B1 -> uint32 [cout][kh][kw][ceil(cin/32)];
+ *            QNNB_WFMT_F32 (mode QNNB_W_FLOAT: the kernel values themselves, re-laid out) -> float [cout][kh][kw][cin_pad]
  *   scratch: >= 2 floats of device memory (ternary cutoff); may be NULL for the other modes.
  */
 int qnnb_pack_weights(int32_t mode, int32_t nb, float H, const float* w_hwio,

@@ -81,6 +81,8 @@ def weight_levels(kernel, wkind, nb, H=1.0):
         return binarize_levels(kernel, H), float(H)
     if wkind == "ternary":
         return ternarize_levels(kernel, H), float(H)
+    if wkind == "float":                                   # no quantiser (keras Conv2D / Dense): the values themselves
+        return np.asarray(kernel, np.float64), 1.0
     raise ValueError(wkind)
 
 
@@ -237,7 +239,11 @@ def forward(nodes, x, return_all=False, teacher=None):
             vals[i] = QT(t.kind, np.pad(t.data, ((0, 0), (p, p), (p, p), (0, 0))), t.scale)
         elif op in ("conv", "dense"):
             lv, ws = weight_levels(nd["kernel"], nd["wkind"], nd["nb"], nd["H"])
-            c, iacc = linear(src[0], lv, ws, nd.get("stride", 1), dense=(op == "dense"))
+            xin = src[0]
+            if nd["wkind"] == "float" and xin.kind != "f32":
+                # a float layer sees VALUES; pixel levels become x / 255 in fp32 as utils/load_data.py:40 computes them
+                xin = QT("f32", (xin.data.astype(F32) / F32(255)).astype(F32)) if xin.kind == "u8" else QT("f32", xin.values())
+            c, iacc = linear(xin, lv, ws, nd.get("stride", 1), dense=(op == "dense"))
             if iacc is not None:
                 info["acc"][i] = iacc
             if nd["use_bias"]:

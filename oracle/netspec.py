@@ -26,6 +26,7 @@ _KINDS = {
     "full-bnn": ("binary", "binary"),
     "tnn": ("ternary", "leaky"),
     "qtnn": ("ternary", "quant"),
+    "float": ("float", "leaky"),            # plain Conv2D / Dense, model_factory.py:24-27
 }
 
 

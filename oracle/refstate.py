@@ -59,6 +59,8 @@ def _weights(nd):
         return quantize(k, nd["nb"])
     if nd["wkind"] == "binary":
         return binarize(k, nd["H"])
+    if nd["wkind"] == "float":                     # keras Conv2D / Dense (model_factory.py:24-27): no quantiser
+        return k
     return ternarize(k, nd["H"])
 
 

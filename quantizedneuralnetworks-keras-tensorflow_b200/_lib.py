@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("QNNB_LIB") or os.path.join(_HERE, "libqnnb200.so")
 
 # ---- constants mirrored from include/qnnb200.h
 KIND_NONE, KIND_U8, KIND_I8, KIND_B1, KIND_F32 = -1, 0, 1, 2, 3
-W_QUANT, W_BINARY, W_TERNARY = 0, 1, 2
-WFMT_I8, WFMT_B1 = 0, 1
+W_QUANT, W_BINARY, W_TERNARY, W_FLOAT = 0, 1, 2, 3
+WFMT_I8, WFMT_B1, WFMT_F32 = 0, 1, 2
 ACT_NONE, ACT_QUANT, ACT_SIGN, ACT_LEAKY, ACT_SIGN_I8 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_GENERIC, IMPL_TCGEN05, IMPL_TCGEN05_V1 = 0, 1, 2, 3
 EINVAL, ECUDA, EUNSUPPORTED = -1, -2, -3
@@ -47,6 +47,7 @@ class ConvDesc(C.Structure):
         ("in_kind", C.c_int32),
         ("impl", C.c_int32),
         ("epi", Epilogue),
+        ("w_f32", C.c_int32),
     ]
 
 
@@ -57,6 +58,7 @@ class DenseDesc(C.Structure):
         ("softmax", C.c_int32),
         ("epi", Epilogue),
         ("avg_positions", C.c_int32),
+        ("w_f32", C.c_int32),
     ]
 
 

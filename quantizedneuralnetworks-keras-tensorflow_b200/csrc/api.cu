@@ -40,6 +40,7 @@ static int validate_conv(const qnnb_conv_desc& d) {
   QNNB_CHECK_ARG(d.stride == 1 || d.stride == 2, "conv2d: stride %d not in {1,2}", d.stride);
   QNNB_CHECK_ARG(d.in_kind == QNNB_KIND_U8 || d.in_kind == QNNB_KIND_I8 || d.in_kind == QNNB_KIND_B1 || d.in_kind == QNNB_KIND_F32,
                  "conv2d: bad in_kind %d", d.in_kind);
+  QNNB_CHECK_ARG(d.w_f32 == 0 || (d.w_f32 == 1 && d.in_kind == QNNB_KIND_F32), "conv2d: an fp32 kernel (w_f32) needs fp32 activations");
   int rc = validate_epilogue(d.epi, true, true);
   if (rc) return rc;
   if (d.epi.pool) {
@@ -76,6 +77,7 @@ int64_t qnnb_packed_weight_bytes(int32_t wfmt, int32_t kh, int32_t kw, int32_t c
   if (kh <= 0 || kw <= 0 || cin <= 0 || cout <= 0) return 0;
   if (wfmt == QNNB_WFMT_I8) return (int64_t)cout * kh * kw * ((cin + 3) / 4 * 4);
   if (wfmt == QNNB_WFMT_B1) return (int64_t)cout * kh * kw * ((cin + 31) / 32) * 4;
+  if (wfmt == QNNB_WFMT_F32) return (int64_t)cout * kh * kw * ((cin + 3) / 4 * 4) * 4;
   return 0;
 }
 
@@ -87,6 +89,7 @@ int qnnb_pack_weights(int32_t mode, int32_t nb, float H, const float* w_hwio, in
 int qnnb_conv2d_tc_supported(const qnnb_conv_desc* d) {
   if (!d || validate_conv(*d) != QNNB_OK) return 0;
   const char* why = "";
+  if (d->w_f32) return 0;                  /* fp32 kernels: CUDA-core FFMA path only */
   if (d->in_kind == QNNB_KIND_F32) return conv_f32_tc_supported(*d, &why) ? 1 : 0;
   return conv_tc_supported(*d, &why) ? 1 : 0;
 }
@@ -111,6 +114,11 @@ int qnnb_conv2d(const qnnb_conv_desc* d, const void* x, const void* w, void* y, 
   QNNB_CHECK_ARG(x && w && y, "conv2d: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const char* why = "";
+  if (d->w_f32) {
+    // 'float' networks: fp32 kernel x fp32 activations on the FFMA path (K4's bf16 split is exact for LEVELS only)
+    if (d->impl == QNNB_IMPL_TCGEN05 || d->impl == QNNB_IMPL_TCGEN05_V1) { set_error("conv2d: fp32 kernels have no tcgen05 path"); return QNNB_EUNSUPPORTED; }
+    return launch_conv_generic(*d, x, w, y, st);
+  }
   if (d->in_kind == QNNB_KIND_F32 && (d->impl == QNNB_IMPL_AUTO || d->impl == QNNB_IMPL_TCGEN05)) {
     // fp32 activations: bf16-split tensor-core kernel where the shape allows it
     if (conv_f32_tc_supported(*d, &why)) return launch_conv_f32_tc(*d, x, w, y, st);
@@ -144,6 +152,7 @@ int qnnb_dense(const qnnb_dense_desc* d, const void* x, const void* w, float* y,
   int rc = validate_epilogue(d->epi, false, false);
   if (rc) return rc;
   QNNB_CHECK_ARG(d->epi.act == QNNB_ACT_NONE, "dense: fused activation not supported (act=%d)", d->epi.act);
+  QNNB_CHECK_ARG(d->w_f32 == 0 || (d->w_f32 == 1 && d->in_kind == QNNB_KIND_F32), "dense: an fp32 kernel (w_f32) needs fp32 input");
   QNNB_CHECK_ARG(d->avg_positions >= 0 && (d->avg_positions <= 1 || d->in_kind == QNNB_KIND_F32),
                  "dense: avg_positions=%d needs fp32 input", d->avg_positions);
   if (d->n == 0) return QNNB_OK;

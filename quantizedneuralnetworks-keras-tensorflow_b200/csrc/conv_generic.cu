@@ -41,6 +41,7 @@ struct ConvP {
   int tiles_y, tiles_x;
   int kwords;        // K words per tap (int8: cin_pad/4, b1: ceil(cin/32), f32: cin)
   int cin_pad;       // int8 weight row pitch in bytes
+  int w_f32;         // KIND_F32: the packed kernel holds fp32 values (QNNB_WFMT_F32, row pitch cin_pad floats) instead of int8 levels
   const void* x;
   const void* wts;
   void* y;
@@ -176,11 +177,17 @@ conv_generic_kernel(const ConvP p) {
         uint32_t wd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (co < p.cout) {
           if constexpr (KIND == QNNB_KIND_F32) {
-            const uint2 raw = __ldg(reinterpret_cast<const uint2*>((const int8_t*)p.wts + ((long long)co * taps + t) * p.cin_pad + k0));
+            if (p.w_f32) {
+              const uint4* src = reinterpret_cast<const uint4*>((const float*)p.wts + ((long long)co * taps + t) * p.cin_pad + k0);
+              const uint4 a = __ldg(src), b = __ldg(src + 1);
+              wd[0] = a.x; wd[1] = a.y; wd[2] = a.z; wd[3] = a.w; wd[4] = b.x; wd[5] = b.y; wd[6] = b.z; wd[7] = b.w;
+            } else {
+              const uint2 raw = __ldg(reinterpret_cast<const uint2*>((const int8_t*)p.wts + ((long long)co * taps + t) * p.cin_pad + k0));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t word = k < 4 ? raw.x : raw.y;
-              wd[k] = __float_as_uint((float)(int)(int8_t)(word >> (8 * (k & 3))));
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t word = k < 4 ? raw.x : raw.y;
+                wd[k] = __float_as_uint((float)(int)(int8_t)(word >> (8 * (k & 3))));
+              }
             }
           } else {
             const uint4* src = reinterpret_cast<const uint4*>((const uint32_t*)p.wts + ((long long)co * taps + t) * p.kwords + k0);
@@ -201,8 +208,8 @@ conv_generic_kernel(const ConvP p) {
       uint32_t v = 0;
       if (k < kc && co < p.cout) {
         if constexpr (KIND == QNNB_KIND_F32) {
-          const int8_t* wb = (const int8_t*)p.wts + ((long long)co * taps + t) * p.cin_pad + (k0 + k);
-          v = __float_as_uint((float)__ldg(wb));
+          const long long wi = ((long long)co * taps + t) * p.cin_pad + (k0 + k);
+          v = p.w_f32 ? __float_as_uint(__ldg((const float*)p.wts + wi)) : __float_as_uint((float)__ldg((const int8_t*)p.wts + wi));
         } else {
           v = __ldg((const uint32_t*)p.wts + ((long long)co * taps + t) * p.kwords + (k0 + k));
         }
@@ -343,6 +350,7 @@ int launch_conv_generic(const qnnb_conv_desc& d, const void* x, const void* w, v
   p.tiles_y = ceil_div(p.oh, tc == 16 ? Tile<16>::TPY : (tc == 32 ? Tile<32>::TPY : Tile<64>::TPY));
   p.tiles_x = ceil_div(p.ow, tc == 16 ? Tile<16>::TPX : (tc == 32 ? Tile<32>::TPX : Tile<64>::TPX));
   p.cin_pad = (d.cin + 3) / 4 * 4;
+  p.w_f32 = d.w_f32;
   if (d.in_kind == QNNB_KIND_F32) p.kwords = d.cin;
   else if (d.in_kind == QNNB_KIND_B1) p.kwords = (d.cin + 31) / 32;
   else p.kwords = p.cin_pad / 4;

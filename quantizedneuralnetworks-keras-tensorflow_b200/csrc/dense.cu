@@ -24,6 +24,7 @@ struct DenseP {
   float* y;
   float* logits;
   int softmax;
+  int w_f32;         // fp32 input: the packed kernel holds fp32 values (QNNB_WFMT_F32)
   Epi epi;
 };
 
@@ -46,7 +47,10 @@ dense_kernel(const DenseP p) {
           const float xv = __ldg(xr + k);
 #pragma unroll
           for (int u = 0; u < UG; ++u)
-            if (u < ug) acc[u] = fmaf(xv, (float)__ldg((const int8_t*)p.w + (long long)(u0 + u) * p.fin_pad + k), acc[u]);
+            if (u < ug) {
+              const long long wi = (long long)(u0 + u) * p.fin_pad + k;
+              acc[u] = fmaf(xv, p.w_f32 ? __ldg((const float*)p.w + wi) : (float)__ldg((const int8_t*)p.w + wi), acc[u]);
+            }
         }
 #pragma unroll
         for (int u = 0; u < UG; ++u) {
@@ -238,7 +242,10 @@ dense_avgpool_f32_kernel(const DenseP p, int positions) {
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) {
         const int c = lane + 32 * j;
-        if (j < nj && c < p.fin) part = fmaf(s[j], (float)__ldg((const int8_t*)p.w + (long long)u * p.fin_pad + c), part);
+        if (j < nj && c < p.fin) {
+          const long long wi = (long long)u * p.fin_pad + c;
+          part = fmaf(s[j], p.w_f32 ? __ldg((const float*)p.w + wi) : (float)__ldg((const int8_t*)p.w + wi), part);
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -270,7 +277,7 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
   if (d.in_kind == QNNB_KIND_B1) p.kwords = (d.fin + 31) / 32;
   else p.kwords = p.fin_pad / 4;
   QNNB_CHECK_ARG(d.in_kind != QNNB_KIND_I8 || (d.fin & 3) == 0, "dense: int8 input needs fin %% 4 == 0 (got %d)", d.fin);
-  p.x = x; p.w = w; p.y = y; p.logits = logits; p.softmax = d.softmax;
+  p.x = x; p.w = w; p.y = y; p.logits = logits; p.softmax = d.softmax; p.w_f32 = d.w_f32;
   p.epi = make_epi(d.epi);
   int blocks = ceil_div(d.n, 8);
   if (blocks < 1) blocks = 1;

@@ -92,12 +92,33 @@ __global__ void pack_b1_kernel(int mode, float qm, float H, const float* __restr
   out[i] = bits;
 }
 
+// 'float' networks (plain Conv2D / Dense, models/model_factory.py:24-27): no quantiser, the kernel values re-laid out
+// K-major like the level formats: out[co][tap][ci_pad], zero filled
+__global__ void pack_f32_kernel(const float* __restrict__ w, int taps, int cin, int cin_pad, int cout, float* __restrict__ out) {
+  long long total = (long long)cout * taps * cin_pad;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ci = (int)(i % cin_pad);
+  long long r = i / cin_pad;
+  int tap = (int)(r % taps);
+  int co = (int)(r / taps);
+  out[i] = ci < cin ? w[((long long)tap * cin + ci) * cout + co] : 0.f;
+}
+
 int launch_pack_weights(int mode, int nb, float H, const float* w, int kh, int kw, int cin, int cout,
                         int wfmt, void* out, float* scratch, cudaStream_t st) {
-  QNNB_CHECK_ARG(mode == QNNB_W_QUANT || mode == QNNB_W_BINARY || mode == QNNB_W_TERNARY, "pack_weights: bad mode %d", mode);
-  QNNB_CHECK_ARG(wfmt == QNNB_WFMT_I8 || wfmt == QNNB_WFMT_B1, "pack_weights: bad wfmt %d", wfmt);
+  QNNB_CHECK_ARG(mode == QNNB_W_QUANT || mode == QNNB_W_BINARY || mode == QNNB_W_TERNARY || mode == QNNB_W_FLOAT, "pack_weights: bad mode %d", mode);
+  QNNB_CHECK_ARG(wfmt == QNNB_WFMT_I8 || wfmt == QNNB_WFMT_B1 || wfmt == QNNB_WFMT_F32, "pack_weights: bad wfmt %d", wfmt);
+  QNNB_CHECK_ARG((mode == QNNB_W_FLOAT) == (wfmt == QNNB_WFMT_F32), "pack_weights: QNNB_W_FLOAT and QNNB_WFMT_F32 come together");
   QNNB_CHECK_ARG(w && out, "pack_weights: null pointer");
   QNNB_CHECK_ARG(kh > 0 && kw > 0 && cin > 0 && cout > 0, "pack_weights: bad shape %dx%dx%dx%d", kh, kw, cin, cout);
+  if (mode == QNNB_W_FLOAT) {
+    const int cin_pad = (cin + 3) / 4 * 4;
+    const long long total = (long long)cout * kh * kw * cin_pad;
+    pack_f32_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(w, kh * kw, cin, cin_pad, cout, (float*)out);
+    QNNB_CUDA(cudaGetLastError());
+    return QNNB_OK;
+  }
   QNNB_CHECK_ARG(mode != QNNB_W_QUANT || (nb >= 2 && nb <= 8), "pack_weights: nb=%d outside 2..8 (int8 levels)", nb);
   QNNB_CHECK_ARG(wfmt != QNNB_WFMT_B1 || mode == QNNB_W_BINARY, "pack_weights: 1-bit format needs binary weights");
   QNNB_CHECK_ARG(H > 0.f, "pack_weights: H must be > 0");

@@ -74,6 +74,8 @@ def pack_weights(kernel_hwio: torch.Tensor, mode: int, nb: int, H: float, wfmt: 
                                       L.ptr(out), L.ptr(scratch), L.current_stream_ptr()))
     if wfmt == L.WFMT_I8:
         return out.view(torch.int8).reshape(cout, kh, kw, (cin + 3) // 4 * 4)
+    if wfmt == L.WFMT_F32:
+        return out.view(torch.float32).reshape(cout, kh, kw, (cin + 3) // 4 * 4)
     return out.view(torch.int32).reshape(cout, kh, kw, (cin + 31) // 32)
 
 
@@ -119,6 +121,7 @@ def _conv_desc(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, impl) -> L.Con
     d.in_kind = KIND_CODE[x.kind]
     d.impl = int(impl)
     d.epi = epi
+    d.w_f32 = 0
     return d
 
 
@@ -133,8 +136,10 @@ def conv2d_on_tensor_cores(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, im
 
 def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epilogue, impl=L.IMPL_AUTO,
            out: torch.Tensor | None = None) -> QTensor:
+    """``w_packed`` of dtype float32 is a QNNB_WFMT_F32 kernel ('float' networks; fp32 activations only)."""
     n, h, w, cin = (int(v) for v in x.shape)
     d = _conv_desc(x, kh, kw, cout, stride, epi, impl)
+    d.w_f32 = 1 if w_packed.dtype == torch.float32 else 0
     oh, ow = C.c_int32(), C.c_int32()
     L.check(L.lib().qnnb_conv2d_out_shape(C.byref(d), C.byref(oh), C.byref(ow)))
     oh, ow = oh.value, ow.value
@@ -171,6 +176,7 @@ def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=Fa
     d.in_kind = KIND_CODE[x.kind]
     d.softmax = 1 if softmax else 0
     d.epi = epi
+    d.w_f32 = 1 if w_packed.dtype == torch.float32 else 0
     dev = x.data.device
     if out is None:
         out = torch.empty((n, units), dtype=torch.float32, device=dev)

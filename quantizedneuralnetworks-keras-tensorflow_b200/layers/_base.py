@@ -51,7 +51,7 @@ def _act_spec(activation):
 
 class QLinearBase(Layer):
     """Fields common to conv and dense: weight quantiser, H, multipliers."""
-    WEIGHT_KIND = None          # 'quantized' | 'binary' | 'ternary'
+    WEIGHT_KIND = None          # 'quantized' | 'binary' | 'ternary' | 'float'
 
     def _init_common(self, H, nb, kernel_lr_multiplier, bias_lr_multiplier, use_bias, activation,
                      kernel_initializer, bias_initializer, kernel_regularizer, bias_regularizer,
@@ -84,6 +84,8 @@ class QLinearBase(Layer):
             return L.W_QUANT, nb, 1.0, 1.0 / float(1 << (nb - 1))
         if self.WEIGHT_KIND == "binary":
             return L.W_BINARY, 1, float(self.H), float(self.H)
+        if self.WEIGHT_KIND == "float":
+            return L.W_FLOAT, 0, 1.0, 1.0
         return L.W_TERNARY, 2, float(self.H), float(self.H)
 
     def _resolve_glorot(self, nb_input, nb_output):
@@ -207,6 +209,9 @@ class QConv2DBase(QLinearBase):
         if wfmt == L.WFMT_B1 and self.WEIGHT_KIND != "binary":
             x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
             wfmt = L.WFMT_I8
+        if self.WEIGHT_KIND == "float":
+            x = x if x.kind == "f32" else K.QTensor("f32", x.to_float(), 1.0, x.channels)
+            wfmt = L.WFMT_F32
         dev = x.data.device
         _, _, _, wscale = self.weight_mode()
         scale = K.acc_scale(x.scale if x.kind in ("u8", "i8") else 1.0, wscale)
@@ -259,6 +264,9 @@ class QDenseBase(QLinearBase):
         if wfmt == L.WFMT_B1 and (self.WEIGHT_KIND != "binary" or x.channels % 32):
             x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
             wfmt = L.WFMT_I8
+        if self.WEIGHT_KIND == "float":
+            x = x if x.kind == "f32" else K.QTensor("f32", x.to_float(), 1.0, x.channels)
+            wfmt = L.WFMT_F32
         dev = x.data.device
         _, _, _, wscale = self.weight_mode()
         scale = K.acc_scale(x.scale if x.kind == "i8" else 1.0, wscale)

@@ -7,8 +7,8 @@ kernel_initializer, kernel_regularizer`` (config/config.py, test_resnet.py:48-62
 Differences from the reference, all deliberate:
 * ``Fc`` accepts ``units`` positionally: models/vgg.py:41 calls ``Fc(cf.classes)``, which the
   reference's ``lambda **kwargs`` (model_factory.py:31) cannot take (SURVEY.md finding 6);
-* ``float`` and ``full-tnn`` raise ``NotImplementedError``: plain fp32 layers and the batch-global
-  ``ternary_tanh`` are outside the accelerated path;
+* ``full-tnn`` raises ``NotImplementedError``: ``ternary_tanh`` thresholds on a whole-BATCH mean
+  (ternary_ops.py:52-54), which no batch-sharded or chunked forward can reproduce;
 * ``model.summary()`` is only printed when ``cf.verbose`` is truthy.
 """
 from ..engine import Activation, LeakyReLU
@@ -17,10 +17,11 @@ from ..layers.quantized_ops import quantized_tanh as quantize_op
 from ..layers.binary_layers import BinaryConv2D, BinaryDense
 from ..layers.binary_ops import binary_tanh
 from ..layers.ternary_layers import TernaryConv2D, TernaryDense
+from ..layers.float_layers import Conv2D, Dense
 from .resnet import ResNet18
 from .vgg import Vgg
 
-NETWORK_TYPES = ('qnn', 'full-qnn', 'bnn', 'qbnn', 'full-bnn', 'tnn', 'qtnn')
+NETWORK_TYPES = ('float', 'qnn', 'full-qnn', 'bnn', 'qbnn', 'full-bnn', 'tnn', 'qtnn')
 
 
 def build_model(cf, legacy_resnet=False):
@@ -31,7 +32,9 @@ def build_model(cf, legacy_resnet=False):
     quant = lambda: Activation(quantized_relu)
     kind = cf.network_type
 
-    if kind in ('qnn', 'full-qnn'):
+    if kind == 'float':
+        Conv, Fc, Act = Conv2D, Dense, leaky                                 # model_factory.py:24-27
+    elif kind in ('qnn', 'full-qnn'):
         Conv = lambda **kw: QuantizedConv2D(H=1, nb=cf.wbits, **kw)
         Fc = lambda *a, **kw: QuantizedDense(*a, nb=cf.abits, **kw)      # nb=abits as in the reference
         Act = leaky if kind == 'qnn' else quant
@@ -43,9 +46,9 @@ def build_model(cf, legacy_resnet=False):
         Conv = lambda **kw: TernaryConv2D(H=1, **kw)
         Fc = TernaryDense
         Act = leaky if kind == 'tnn' else quant
-    elif kind in ('float', 'full-tnn'):
-        raise NotImplementedError("network_type %r is outside the accelerated path (plain fp32 layers / "
-                                  "batch-global ternary_tanh); supported: %s" % (kind, ", ".join(NETWORK_TYPES)))
+    elif kind == 'full-tnn':
+        raise NotImplementedError("network_type %r is outside the accelerated path (batch-global ternary_tanh); "
+                                  "supported: %s" % (kind, ", ".join(NETWORK_TYPES)))
     else:
         raise ValueError('wrong network type, the supported network types in this repo are float, qnn, full-qnn, bnn and full-bnn')
 

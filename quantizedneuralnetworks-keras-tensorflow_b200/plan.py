@@ -233,6 +233,10 @@ class Plan:
         if x.kind == "b1" and lay.WEIGHT_KIND != "binary":
             x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
         wfmt = L.WFMT_B1 if x.kind == "b1" else L.WFMT_I8
+        if lay.WEIGHT_KIND == "float":
+            # plain Conv2D ('float' networks): fp32 kernel x fp32 values; pixel levels become level / 255 first
+            x = x if x.kind == "f32" else K.QTensor("f32", x.to_float(), 1.0, x.channels)
+            wfmt = L.WFMT_F32
         _, _, _, wscale = lay.weight_mode()
         scale = K.acc_scale(x.scale if x.kind in ("u8", "i8") else 1.0, wscale)
         inv = shift = None
@@ -293,6 +297,9 @@ class Plan:
         if x.kind == "i8" and x.channels % 4 != 0:
             x = K.QTensor("f32", x.to_float(), 1.0, x.channels)
         wfmt = L.WFMT_B1 if x.kind == "b1" else L.WFMT_I8
+        if lay.WEIGHT_KIND == "float":
+            x = x if x.kind == "f32" else K.QTensor("f32", x.to_float(), 1.0, x.channels)
+            wfmt = L.WFMT_F32
         n = int(x.data.shape[0])
         ch = x.channels
         flat_shape = x.shape[1:]
@@ -364,6 +371,8 @@ class Plan:
         for st in self.steps[:-1]:
             lay = st.layer
             if st.src != prev or st.res is not None or st.act is None or st.act[0] not in ("quant", "binary"):
+                return None
+            if lay.WEIGHT_KIND == "float":
                 return None
             if tuple(lay.kernel_size) != (3, 3) or tuple(lay.strides) != (1, 1):
                 return None

@@ -116,6 +116,21 @@ class Conv2D(Layer):
         self.kernel_regularizer, self.bias_regularizer = kernel_regularizer, bias_regularizer
         self.activity_regularizer, self.kernel_constraint, self.bias_constraint = activity_regularizer, kernel_constraint, bias_constraint
 
+    # keras.layers.Conv2D itself (network_type 'float', models/model_factory.py:24-25); the reference's custom layers
+    # override build / call
+    def build(self, input_shape):
+        cin = int(input_shape[-1])
+        self.kernel = self.add_weight(shape=self.kernel_size + (cin, self.filters), initializer=self.kernel_initializer, name="kernel")
+        self.bias = self.add_weight(shape=(self.filters,), initializer=self.bias_initializer, name="bias") if self.use_bias else None
+        self.built = True
+
+    def call(self, x):
+        from .. import backend as K
+        y = K.conv2d(x, self.kernel, strides=self.strides, padding=self.padding, data_format=self.data_format, dilation_rate=self.dilation_rate)
+        if self.use_bias:
+            y = K.bias_add(y, self.bias, data_format=self.data_format)
+        return self.activation(y) if self.activation is not None else y
+
     def get_config(self):
         return {"name": self.name, "filters": self.filters}
 
@@ -129,6 +144,19 @@ class Dense(Layer):
         self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
         self.kernel_regularizer, self.bias_regularizer = kernel_regularizer, bias_regularizer
         self.activity_regularizer, self.kernel_constraint, self.bias_constraint = activity_regularizer, kernel_constraint, bias_constraint
+
+    # keras.layers.Dense itself (network_type 'float')
+    def build(self, input_shape):
+        self.kernel = self.add_weight(shape=(int(input_shape[-1]), self.units), initializer=self.kernel_initializer, name="kernel")
+        self.bias = self.add_weight(shape=(self.units,), initializer=self.bias_initializer, name="bias") if self.use_bias else None
+        self.built = True
+
+    def call(self, x):
+        from .. import backend as K
+        y = K.dot(x, self.kernel)
+        if self.use_bias:
+            y = K.bias_add(y, self.bias)
+        return self.activation(y) if self.activation is not None else y
 
     def get_config(self):
         return {"name": self.name, "units": self.units}

@@ -125,6 +125,9 @@ MODEL_CASES = {
     "resnet1_fullqnn_w4a4": (dict(network_type='full-qnn', wbits=4, abits=4, architecture='RESNET', nres=1), 4, 9, "spread"),
     "resnet1_tnn": (dict(network_type='tnn', wbits=4, abits=4, architecture='RESNET', nres=1), 4, 10, "spread"),
     "resnet1_qbnn_a4": (dict(network_type='qbnn', wbits=4, abits=4, architecture='RESNET', nres=1), 4, 11, "spread"),
+    # network_type 'float': keras Conv2D / Dense / LeakyReLU (model_factory.py:24-27)
+    "vgg_float": (dict(network_type='float', architecture='VGG'), 4, 12, "spread"),
+    "resnet1_float": (dict(network_type='float', architecture='RESNET', nres=1), 4, 13, "spread"),
 }
 
 
@@ -157,10 +160,12 @@ def fix_vgg_fc_quirk(cf):
     mf.Vgg = patched
 
 
-def gen_models():
+def gen_models(only=None):
     import models.model_factory  # noqa: F401
     fix_vgg_fc_quirk(None)
     for name, (cfkw, batch, seed, bn) in MODEL_CASES.items():
+        if only and name not in only:
+            continue
         KL.reset_names()
         KI.seed(seed)
         cf = make_cf(**cfkw)
@@ -168,7 +173,7 @@ def gen_models():
         nodes = netspec.build_spec(cf)
         netspec.set_weights(nodes, netspec.random_weights(nodes, seed=seed, bias_range=0.1, bn=bn))
         # copy the seeded weights into the reference model, matching layers by creation order (= name suffix)
-        lin = [l for l in model.layers if hasattr(l, "kernel_lr_multiplier")]
+        lin = [l for l in model.layers if hasattr(l, "kernel_lr_multiplier") or type(l).__name__ in ("Conv2D", "Dense")]
         bns = [l for l in model.layers if type(l).__name__ == "BatchNormalization"]
         lin.sort(key=lambda l: int(l.name.rsplit("_", 1)[1]) + (10000 if "dense" in l.name else 0))
         bns.sort(key=lambda l: int(l.name.rsplit("_", 1)[1]))
@@ -177,7 +182,8 @@ def gen_models():
         assert len(lin) == len(spec_lin) and len(bns) == len(spec_bn), (name, len(lin), len(spec_lin), len(bns), len(spec_bn))
         for lay, nd in zip(lin, spec_lin):
             lay.set_weights([nd["kernel"]] + ([nd["bias"]] if nd["use_bias"] else []))
-            assert abs(float(lay.kernel_lr_multiplier) - float(nd.get("klm", lay.kernel_lr_multiplier))) < 1e-3 or nd["op"] == "dense"
+            if hasattr(lay, "kernel_lr_multiplier"):
+                assert abs(float(lay.kernel_lr_multiplier) - float(nd.get("klm", lay.kernel_lr_multiplier))) < 1e-3 or nd["op"] == "dense"
         for lay, nd in zip(bns, spec_bn):
             lay.set_weights([nd["gamma"], nd["beta"], nd["mean"], nd["var"]])
         pyfloat_multipliers(model.layers)
@@ -199,6 +205,9 @@ def gen_models():
 
 
 if __name__ == "__main__":
-    gen_ops()
-    gen_layers()
-    gen_models()
+    if len(sys.argv) > 1:                     # python make_golden.py model_name ... : only these model fixtures
+        gen_models(set(sys.argv[1:]))
+    else:
+        gen_ops()
+        gen_layers()
+        gen_models()

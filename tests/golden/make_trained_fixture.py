@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Convert two of the reference's trained checkpoints (results/RESNET3/weights_44.hdf5 = full-qnn w4a4,
-weights_bb.hdf5 = full-bnn; both from the older, biased ResNet revision -- SURVEY.md finding 7) into compact
+weights_bb.hdf5 = full-bnn, weights_ff.hdf5 = float; all from the older, biased ResNet revision -- SURVEY.md finding 7) into compact
 .npz weight lists with the repo's pure-Python HDF5 reader, so that GPU parity can run on REAL weight / BN
 statistics without /root/reference.  Run in the build container only:
 
@@ -19,9 +19,12 @@ REF = os.environ.get("QNNB_REFERENCE", "/root/reference")
 
 import qnn_b200 as q  # noqa: E402
 
-CASES = {"44": ("full-qnn", 4, 4), "bb": ("full-bnn", 4, 4)}
+CASES = {"44": ("full-qnn", 4, 4), "bb": ("full-bnn", 4, 4), "ff": ("float", 4, 4)}
+ONLY = set(sys.argv[1:])
 
 for code, (nt, wb, ab) in CASES.items():
+    if ONLY and code not in ONLY:
+        continue
     cf = types.SimpleNamespace(network_type=nt, wbits=wb, abits=ab, architecture='RESNET', dataset='CIFAR-10', dim=32, channels=3,
                                classes=10, nres=3, pfilt=1, kernel_initializer='he_normal', kernel_regularizer=1e-4)
     q.reset_names()

@@ -352,6 +352,46 @@ def test_trained_reference_checkpoints_bit_exact(code, nt):
         assert rel_err(got, o2b) <= 1e-4 and (got.argmax(1) == o2b.argmax(1)).mean() >= 0.999
 
 
+@pytest.mark.parametrize("arch", ["VGG", "RESNET"])
+def test_float_network_type_tolerance(arch):
+    """network_type 'float' (keras Conv2D / Dense / LeakyReLU, model_factory.py:24-27): fp32 kernels x fp32 activations on
+    the FFMA kernels.  Floating-point accumulation, so the bar is the north_star tolerance against O1 (float64
+    accumulation) and against the fp32 restatement of the reference graph."""
+    cf, model, nodes = build(dict(network_type='float', architecture=arch, nres=2), bn="spread")
+    x = images(cf, 32)
+    want, vals, info = exact.forward(nodes, x, return_all=True)
+    if arch == "RESNET":
+        got, logits = model.predict(x, return_logits=True)
+        assert rel_err(logits, info["logits"]) <= 1e-4
+    else:
+        got = model.predict(x)
+    assert rel_err(got, want) <= 1e-4
+    assert (got.argmax(1) == want.argmax(1)).mean() >= 0.999
+    ref = refstate.forward(nodes, x, trick=True)             # plain layers: no scaling identity either way
+    assert rel_err(got, ref) <= 1e-4
+    # same numbers for a float32 image batch (what the reference is fed: uint8 / 255, utils/load_data.py:40)
+    got_f = model.predict((x.astype(np.float32) / 255))
+    assert rel_err(got_f, want) <= 1e-4
+    assert not model.plan().fused_available(torch.from_numpy(x).cuda())
+
+
+def test_trained_float_checkpoint_tolerance():
+    """The reference's trained float ResNet-20 (results/RESNET3/weights_ff.hdf5, test accuracy 0.8114 in results.out:29)
+    through the fused plan vs both oracles on noise and smooth images."""
+    cf, model, nodes = _trained("ff", "float")
+    rng = np.random.default_rng(78)
+    noise = rng.integers(0, 256, size=(32, 32, 32, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:32, 0:32]
+    smooth = np.stack([np.stack([(127 + 120 * np.sin(xx / (3 + i) + c) * np.cos(yy / (4 + i))) for c in range(3)], -1) for i in range(16)])
+    for x in (noise, smooth.astype(np.uint8)):
+        want, vals, info = exact.forward(nodes, x, return_all=True)
+        got, logits = model.predict(x, return_logits=True)
+        assert rel_err(logits, info["logits"]) <= 1e-4
+        assert (got.argmax(1) == want.argmax(1)).mean() >= 0.999
+        ref = refstate.forward(nodes, x, trick=True)
+        assert rel_err(got, ref) <= 1e-4
+
+
 def test_evaluate_matches_host_metrics():
     cf, model, nodes = _trained("44", "full-qnn")
     x = images(cf, 64)

@@ -14,11 +14,16 @@ F32 = np.float32
 
 
 def test_network_type_switch_and_errors():
-    for nt in ("qnn", "full-qnn", "bnn", "qbnn", "full-bnn", "tnn", "qtnn"):
+    for nt in ("float", "qnn", "full-qnn", "bnn", "qbnn", "full-bnn", "tnn", "qtnn"):
         for arch in ("VGG", "RESNET"):
             q.reset_names()
             m = q.build_model(make_cf(network_type=nt, architecture=arch, nres=1))
             assert m.output_shape == (None, 10)
+    # 'float' is the plain keras Conv2D / Dense (model_factory.py:24-27): same graph, keras layer names, no quantiser fields
+    q.reset_names()
+    m = q.build_model(make_cf(network_type="float", architecture="RESNET", nres=3, kernel_regularizer=1e-4))
+    assert m.layers[0].name == "conv2d_1" and m.layers[-1].name == "dense_1"
+    assert "H" not in m.layers[0].get_config()
     with pytest.raises(ValueError, match="wrong network type"):
         q.build_model(make_cf(network_type="nope"))
     with pytest.raises(ValueError, match="is not supported"):

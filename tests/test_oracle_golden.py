@@ -126,6 +126,9 @@ MODEL_CASES = {
     "resnet1_fullqnn_w4a4": (dict(network_type='full-qnn', wbits=4, abits=4, architecture='RESNET', nres=1), 9, "spread"),
     "resnet1_tnn": (dict(network_type='tnn', wbits=4, abits=4, architecture='RESNET', nres=1), 10, "spread"),
     "resnet1_qbnn_a4": (dict(network_type='qbnn', wbits=4, abits=4, architecture='RESNET', nres=1), 11, "spread"),
+    # network_type 'float' (keras Conv2D / Dense / LeakyReLU, model_factory.py:24-27)
+    "vgg_float": (dict(network_type='float', architecture='VGG'), 12, "spread"),
+    "resnet1_float": (dict(network_type='float', architecture='RESNET', nres=1), 13, "spread"),
 }
 
 
