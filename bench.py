@@ -112,9 +112,12 @@ def plan_work(plan, env):
 
 def ncu_traffic(workload, step_indices, n_steps):
     """DRAM bytes per launch (read + write), averaged over the given kernels of one forward, from the committed
-    Nsight Compute summary of this workload (profiles/r1_ncu_<workload>.csv, one row per launch of one forward)."""
+    Nsight Compute summary of this workload (profiles/r2_ncu_<workload>.csv, else round 1's; one row per launch of one
+    forward)."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_ncu_%s.csv" % workload)
+    path = os.path.join(ROOT, "profiles", "r2_ncu_%s.csv" % workload)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_ncu_%s.csv" % workload)
     if not os.path.exists(path):
         return None
     rows = list(csv.reader(open(path)))
@@ -532,7 +535,7 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     r0 = rows[members[0]]
     achieved = (ops / (kernel_ms * 1e-3) / 1e12) if r0["bound"] == "tensor" else (byts / (kernel_ms * 1e-3) / 1e9)
     roof = {"bound": r0["bound"], "achieved": achieved, "peak": r0["peak"], "unit": r0["unit"], "frac": achieved / r0["peak"],
-            "traffic": None if fused else ncu_traffic(name, members, len(plan.steps)), "kernel": kname, "kernel_ms": kernel_ms,
+            "traffic": ncu_traffic(name, members, len(timed_steps)), "kernel": kname, "kernel_ms": kernel_ms,
             "peak_source": i8_src if r0["bound"] == "tensor" else pk["source"] + " copy bandwidth",
             "share_of_step": float(sum(per[i] for i in members) / max(per.sum(), 1e-30)),
             "algorithmic": {"ops_per_launch": float(ops), "bytes_per_launch": float(byts)},

@@ -1,2 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_models.py -q -x -k "float or trained" > gpurun_out/t9_float.log 2>&1; echo "rc=$?" >> gpurun_out/t9_float.log
-tail -15 gpurun_out/t9_float.log
+for n in 8 4 2; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_${n}gpu.json 2> gpurun_out/r2p_cfg3_${n}gpu.err
+  tail -1 gpurun_out/r2p_final_cfg3_${n}gpu.json | cut -c1-330
+done
+python bench.py --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_1gpu_same_box.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg3_1gpu_same_box.json | cut -c1-330
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 200 --warmup 10 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_8gpu_s200.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg3_8gpu_s200.json | cut -c1-330
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 --workload cfg4 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg4_8gpu.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg4_8gpu.json | cut -c1-330
