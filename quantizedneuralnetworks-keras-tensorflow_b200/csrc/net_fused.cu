@@ -22,9 +22,15 @@
 //     warp pairs take alternate image-row pairs of a block.  2x2 max-pool on the raw accumulators (min where the BN slope
 //     is negative), then the fixed fp32 op order of common.cuh (qaffine / quant_scaled, or the binary_tanh threshold),
 //     and the level byte goes straight into the NEXT layer's raster (or the flat HWC feature vector of the dense head).
-//   * Warp roles (512 threads): warps with (id % 4) < 2 -> epilogue; warp 2 -> one elected MMA-issuing thread; the other
-//     seven -> image fetch (bulk copy, double buffered), first-layer im2col of the NEXT image while this one is in
-//     flight, and the dense head (dp4a + warp reduce, fp32 affine) of the PREVIOUS image.
+//   * Pooled first layer (the bulk of the accumulators: 50 k of cfg1's 66 k per image): operands swapped -- M = 128 POOLED
+//     pixels, N = the kernel's 64 rows, and one MMA per 2x2 window position into its own 64 accumulator columns (the
+//     im2col rows are written position-major).  Thread = pooled pixel: all four SM sub-partitions work, the pool is a
+//     max over four columns of the same lane, a warp handles 16 channels and its 16 level bytes leave as ONE 16-byte
+//     store into the next raster (per-channel constants are broadcast shared-memory loads).
+//   * Warp roles (544 threads): warp 16 -> one elected MMA-issuing thread; warps 0..15: (id % 4) < 2 -> epilogue of
+//     layers 1.., the others -> image fetch (bulk copy, double buffered), first-layer im2col of the NEXT image while
+//     this one is in flight, and the dense head (dp4a + warp reduce, fp32 affine) of the PREVIOUS image; all sixteen
+//     share the pooled first layer's epilogue.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -36,11 +42,12 @@ namespace {
 
 using namespace tcx;
 
-constexpr int NF_THREADS = 512;
+constexpr int NF_THREADS = 544;           // 16 epilogue / worker warps + the MMA-issuing warp 16
 constexpr int NF_MAXL = QNNB_NET_MAX_CONVS;
 constexpr int NF_ABLK = 2048;            // one A block: 64 kernel rows x 32 K bytes (the MMA reads 128 rows: the next block)
-constexpr int NF_WORKERS = 7;            // worker warps
+constexpr int NF_WORKERS = 8;            // worker warps: ids with (id % 4) >= 2 among the first 16
 constexpr int NF_SMEM_MAX = 232448;
+constexpr int NF_MMA_WARP = 16;
 
 struct NfLayer {
   int h, w, cin, cout;
@@ -51,6 +58,8 @@ struct NfLayer {
   int out_off, out_plane, out_wp;      // next raster; out_plane == 0: flat [pixel][cout] feature vector
   int a_off;               // A blocks of this layer
   int cin_pad;             // channel pitch of the packed kernel
+  int posmajor;            // pooled first layer: pixels on M, one MMA per 2x2 window position (see nf_first_pooled)
+  int ppw, npp, mtiles;    // posmajor: pooled width, pooled pixels, 128-row M tiles
   float qm, acc_scale;
   const int8_t* wpk;
   const float *bias, *bn_inv, *bn_shift;
@@ -213,16 +222,62 @@ __device__ __forceinline__ void nf_epi_block(uint32_t taddr, int pair, int rows,
   }
 }
 
+// Pooled first layer with pixels on M (see the file header): this warp's lane quarter (32 pooled pixels of each M tile) x
+// the 16 channels of group g = warp / 4.  Accumulator columns of M tile mt: [mt * 256 + pos * 64 + channel], pos = the 2x2
+// window position.  cst: the layer's per-channel constants {s, bias, inv * qm, shift * qm} (broadcast loads); the 16 level
+// bytes of a pooled pixel leave as one 16-byte store: next raster plane g, or the flat [pixel][cout] feature vector.
+template <bool SIGN>
+__device__ __forceinline__ void nf_first_pooled(uint32_t tmem_base, int warp, int lane, int mtiles, int npp, int ppw, int cout, float qm,
+                                                const float4* cst, uint8_t* out, int out_plane, int out_wp) {
+  const int quarter = warp & 3, g = warp >> 2;
+  if (16 * g >= cout) return;                                // warp-uniform
+  const uint32_t rcp = (65536u + (uint32_t)ppw - 1u) / (uint32_t)ppw;   // pp / ppw for pp < 2048, ppw <= 16
+  for (int mt = 0; mt < mtiles; ++mt) {
+    const int pp = mt * 128 + quarter * 32 + lane;
+    const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * 256 + 16 * g);
+    int p0[16], p1[16], p2[16], p3[16];
+    __syncwarp();
+    tmem_ld16_nowait(ta, p0);
+    tmem_ld16_nowait(ta + 64, p1);
+    tmem_ld16_nowait(ta + 128, p2);
+    tmem_ld16_nowait(ta + 192, p3);
+    tmem_ld_wait_dep16x4(p0, p1, p2, p3);
+    uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 kc = cst[16 * g + j];
+      QConst qc;
+      qc.s = kc.x; qc.a = kc.y; qc.b = kc.z; qc.c = kc.w;
+      const bool dec = kc.z < 0.f;                           // uniform: one channel per j for the whole warp
+      const int m = dec ? min(min(p0[j], p1[j]), min(p2[j], p3[j])) : max(max(p0[j], p1[j]), max(p2[j], p3[j]));
+      const int lv = nf_level<SIGN>(m, qc, qm);
+      wd[j >> 2] |= (uint32_t)(lv & 0xFF) << (8 * (j & 3));
+    }
+    if (pp < npp) {
+      uint8_t* dst;
+      if (out_plane == 0) {
+        dst = out + pp * cout + 16 * g;
+      } else {
+        const int ph = (int)(((uint32_t)pp * rcp) >> 16), pw = pp - ph * ppw;
+        dst = out + g * out_plane + (((ph + 1) * out_wp + pw + 1) << 4);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  }
+}
+
 // first-layer im2col: pixel (h, w) -> 32 K bytes (tap-major, channel-minor; zero outside the image) at row h * WP + w of
 // the two 16-byte K planes.  The 3 * CIN bytes a filter row needs are contiguous in the raw image: they are cut out of
 // aligned 32-bit words with funnel shifts (byte loads cost ~20 instructions per tap).
-template <int CIN>
+// POS (pooled first layer with pixels on M): four tiles, one per 2x2 window position, row = pooled pixel; tile = 2 planes.
+template <int CIN, bool POS>
 __device__ __forceinline__ void nf_im2col(const uint8_t* raw, uint8_t* dst, int plane, int H, int W, int WP, int wt, int nthreads) {
   const int npix = H * W;
   const uint32_t rcp = (65536u + (uint32_t)W - 1u) / (uint32_t)W;       // n / W == (n * rcp) >> 16 for n < 2048, W <= 32
   const uint32_t* words = reinterpret_cast<const uint32_t*>(raw);       // raw is 16-byte aligned
   for (int n = wt; n < npix; n += nthreads) {
     const int h = (int)(((uint32_t)n * rcp) >> 16), w = n - h * W;
+    if (POS && (h >= (H & ~1) || w >= (W & ~1))) continue;     // the odd last row / column is dropped by the valid pooling
     const bool left = w == 0, right = w == W - 1;
     uint32_t v[3][3];
 #pragma unroll
@@ -263,9 +318,10 @@ __device__ __forceinline__ void nf_im2col(const uint8_t* raw, uint8_t* dst, int 
       wd[6] = (v[2][1] >> 16) | (v[2][2] << 16);
       wd[7] = 0u;
     }
-    const int m = h * WP + w;                                  // row of the im2col tile (pitch WP >= W)
-    *reinterpret_cast<uint4*>(dst + m * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-    if (9 * CIN > 16) *reinterpret_cast<uint4*>(dst + plane + m * 16) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+    // row of the im2col tile: natural order (pitch WP >= W), or [window position][pooled pixel] (WP = pooled width)
+    uint8_t* d = POS ? dst + ((h & 1) * 2 + (w & 1)) * 2 * plane + ((h >> 1) * WP + (w >> 1)) * 16 : dst + (h * WP + w) * 16;
+    *reinterpret_cast<uint4*>(d) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    if (9 * CIN > 16) *reinterpret_cast<uint4*>(d + plane) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
   }
 }
 
@@ -347,6 +403,7 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
   auto featfull = [&](int b) { return bar_base + 64u + 8u * b; };
   auto actfull = [&](int l) { return bar_base + 80u + 8u * l; };
   const uint32_t b_blob = bar_base + 136u;
+  const uint32_t b_c0full = bar_base + 144u;        // pooled first layer: its MMAs have completed
   const uint32_t tmem_slot = bar_base + 160u;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sg + p.bar_off + 160);
 
@@ -360,13 +417,15 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
     mbar_init(b_imfull, NF_WORKERS);
     mbar_init(b_imfree, 1);
     mbar_init(b_blob, 1);
+    mbar_init(b_c0full, 1);
+    const int pm = p.L[0].posmajor;                 // then all 16 warps write the first layer's output
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
       mbar_init(tempty(b), 8);
       mbar_init(rawfull(b), 1);
-      mbar_init(featfull(b), 8);
+      mbar_init(featfull(b), (pm && p.nconv == 1) ? 16 : 8);
     }
-    for (int l = 0; l < NF_MAXL; ++l) mbar_init(actfull(l), 8);
+    for (int l = 0; l < NF_MAXL; ++l) mbar_init(actfull(l), (pm && l == 0) ? 16 : 8);
     fence_barrier_init();
     // the net's resident image: weights only, so it does not wait for the previous kernel
     mbar_expect_tx(b_blob, (uint32_t)p.blob_bytes);
@@ -375,7 +434,7 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
       bulk_load_1d(smem_base + off, p.blob + off, (uint32_t)sz, b_blob);
     }
   }
-  if (warp == 2) {
+  if (warp == NF_MMA_WARP) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -391,7 +450,23 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
 
   const int nloc = p.n > (int)blockIdx.x ? (p.n - (int)blockIdx.x + G - 1) / G : 0;     // images of this CTA
 
-  if (warp == 2) {
+  // the pooled first layer's epilogue, shared by all 16 warps (warp = lane quarter x channel group)
+  auto first_pooled = [&](int k) {
+    const NfLayer& L0 = p.L[0];
+    mbar_wait_parked(b_c0full, (uint32_t)k & 1u);
+    tc_fence_after();
+    const float4* cst = reinterpret_cast<const float4*>(sg + p.cst_off);
+    uint8_t* out = L0.out_plane == 0 ? sg + p.feat_off + (k & 1) * p.feat_stride : sg + L0.out_off;
+    if (L0.sign) nf_first_pooled<true>(tmem_base, warp, lane, L0.mtiles, L0.npp, L0.ppw, L0.cout, L0.qm, cst, out, L0.out_plane, L0.out_wp);
+    else nf_first_pooled<false>(tmem_base, warp, lane, L0.mtiles, L0.npp, L0.ppw, L0.cout, L0.qm, cst, out, L0.out_plane, L0.out_wp);
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p.nconv > 1 ? actfull(0) : featfull(k & 1));
+  };
+  const bool posmajor = p.L[0].posmajor != 0;
+
+  if (warp == NF_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       mbar_wait(b_blob, 0u);
@@ -399,6 +474,25 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
       for (int k = 0; k < nloc; ++k) {
         for (int l = 0; l < p.nconv; ++l) {
           const NfLayer& Ly = p.L[l];
+          if (l == 0 && posmajor) {
+            // pixels on M: A = the position-major im2col tiles (u8), B = the kernel block (64 rows, s8); one MMA per
+            // (M tile, window position) into its own 64 columns.  Both accumulator buffers are used: every reader of
+            // the previous image must be done (its last layer's warps have arrived on featfull).
+            mbar_wait(b_imfull, (uint32_t)k & 1u);
+            if (k > 0) mbar_wait(featfull((k - 1) & 1), (uint32_t)((k - 1) >> 1) & 1u);
+            tc_fence_after();
+            nftrace(p, 10, 0);
+            const uint32_t idesc = make_idesc_i8(128, 64, /*a signed*/ false, /*b signed*/ true);
+            const uint64_t w_desc = make_smem_desc_interleaved(smem_base + Ly.a_off, 128, 256);
+            const uint64_t x_desc = make_smem_desc_interleaved(smem_base + Ly.in_off, Ly.in_plane, 128);
+            for (int mt = 0; mt < Ly.mtiles; ++mt)
+              for (int pos = 0; pos < 4; ++pos)
+                umma_i8(tmem_base + (uint32_t)(mt * 256 + pos * 64), x_desc + (uint64_t)((pos * 2 * Ly.in_plane + mt * 2048) >> 4), w_desc, idesc, 0u);
+            umma_commit(b_c0full);
+            umma_commit(b_imfree);
+            nftrace(p, 12, 0);
+            continue;
+          }
           const int nblk = Ly.nblk, rb = Ly.rb, lh = Ly.h, wp = Ly.wp, nhalf = Ly.cin >> 5;
           // descriptors advance by (bytes >> 4) in their 14-bit address field
           const uint64_t a_desc0 = make_smem_desc_interleaved(smem_base + Ly.a_off, 128, 256);
@@ -454,6 +548,7 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
     uint32_t q = 0;
     for (int k = 0; k < nloc; ++k) {
       for (int l = 0; l < p.nconv; ++l) {
+        if (l == 0 && posmajor) { first_pooled(k); nftrace(p, 21, 0); continue; }
         const NfLayer& Ly = p.L[l];
         const int nblk = Ly.nblk, rb = Ly.rb, lh = Ly.h, lw = Ly.w, wp = Ly.wp, pool = Ly.pool, sign = Ly.sign, cout = Ly.cout;
         const float qm = Ly.qm;
@@ -509,7 +604,7 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
     }
   } else {
     // ===================== workers: image fetch, first-layer im2col, dense head =====================
-    const int wi = (warp >> 2) * 2 + (warp & 3) - 3;          // 0..6
+    const int wi = (warp >> 2) * 2 + (warp & 3) - 2;          // 0..7
     const int wt = wi * 32 + lane;
     const int l0h = p.L[0].h, l0w = p.L[0].w, l0wp = p.L[0].wp, l0cin = p.L[0].cin, im_off = p.L[0].in_off, im_plane = p.L[0].in_plane;
     auto fetch = [&](int k) {
@@ -549,13 +644,19 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
       nftrace(p, 30, k);
       if (k >= 1) mbar_wait_parked(b_imfree, (uint32_t)(k - 1) & 1u);
       const uint8_t* raw = sg + p.raw_off + (k & 1) * p.raw_stride;
-      if (l0cin == 1) nf_im2col<1>(raw, sg + im_off, im_plane, l0h, l0w, l0wp, wt, NF_WORKERS * 32);
-      else nf_im2col<3>(raw, sg + im_off, im_plane, l0h, l0w, l0wp, wt, NF_WORKERS * 32);
+      if (posmajor) {
+        if (l0cin == 1) nf_im2col<1, true>(raw, sg + im_off, im_plane, l0h, l0w, p.L[0].ppw, wt, NF_WORKERS * 32);
+        else nf_im2col<3, true>(raw, sg + im_off, im_plane, l0h, l0w, p.L[0].ppw, wt, NF_WORKERS * 32);
+      } else {
+        if (l0cin == 1) nf_im2col<1, false>(raw, sg + im_off, im_plane, l0h, l0w, l0wp, wt, NF_WORKERS * 32);
+        else nf_im2col<3, false>(raw, sg + im_off, im_plane, l0h, l0w, l0wp, wt, NF_WORKERS * 32);
+      }
       fence_proxy_async();                                    // im2col rows -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(b_imfull);
       nftrace(p, 31, k);
       if (k == 0) mbar_wait_parked(b_blob, 0u);               // the dense kernel / constants are part of the resident image
+      if (posmajor) first_pooled(k);
       if (k >= 1) dense(k - 1);
       nftrace(p, 33, k);
     }
@@ -566,7 +667,7 @@ vgg_fused_kernel(const __grid_constant__ NfParams p) {
   nftrace(p, 40, 0);
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == NF_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -617,6 +718,14 @@ const char* nf_plan(const qnnb_vgg_desc& d, NfParams& p, int& smem_bytes) {
     if (L.pool) rb = (rb + 1) & ~1;
     nblk = (h + rb - 1) / rb;
     L.rb = rb; L.nblk = nblk;
+    if (l == 0 && L.pool) {
+      // pooled first layer: pixels on M, position-major im2col (see nf_first_pooled)
+      L.posmajor = 1;
+      L.ppw = w >> 1;
+      L.npp = (h >> 1) * (w >> 1);
+      L.mtiles = (L.npp + 127) / 128;
+      if (L.mtiles > 2) return "first layer: more than 256 pooled pixels";
+    }
     if (L.pool) { h >>= 1; w >>= 1; }
     cin = c.cout;
   }
@@ -632,8 +741,13 @@ const char* nf_plan(const qnnb_vgg_desc& d, NfParams& p, int& smem_bytes) {
   {
     NfLayer& L = p.L[0];                                // first-layer im2col: two 16-byte K planes of (pixels + 16) rows
     L.in_off = off;
-    L.in_plane = (L.h * L.wp + 16) * 16;
-    off += 2 * L.in_plane;
+    if (L.posmajor) {
+      L.in_plane = L.mtiles * 128 * 16;                 // [position][plane][pooled pixel] x 16 bytes
+      off += 4 * 2 * L.in_plane;
+    } else {
+      L.in_plane = (L.h * L.wp + 16) * 16;
+      off += 2 * L.in_plane;
+    }
   }
   p.zero_off = off;                                     // rasters (inputs of layers 1..): zero-haloed maps, cin / 16 planes
   for (int l = 1; l < d.nconv; ++l) {

@@ -1,7 +1,6 @@
-for n in 8 4 2; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_${n}gpu.json 2> gpurun_out/r2p_cfg3_${n}gpu.err
-  tail -1 gpurun_out/r2p_final_cfg3_${n}gpu.json | cut -c1-330
-done
-python bench.py --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_1gpu_same_box.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg3_1gpu_same_box.json | cut -c1-330
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 200 --warmup 10 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_8gpu_s200.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg3_8gpu_s200.json | cut -c1-330
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 --workload cfg4 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg4_8gpu.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg4_8gpu.json | cut -c1-330
+python bench.py --workload cfg1 --no-cpu-baseline --no-secondary > gpurun_out/u2_cfg1.log 2>gpurun_out/u2_cfg1.err; tail -1 gpurun_out/u2_cfg1.log | cut -c1-900
+python bench.py --workload cfg1 --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/u2_cfg1_s20.log 2>gpurun_out/u2_cfg1_s20.err; tail -1 gpurun_out/u2_cfg1_s20.log | cut -c1-300
+python bench.py --workload cfg1 --streams 2 --no-cpu-baseline --no-secondary > gpurun_out/u2_cfg1_ns2.log 2>/dev/null; tail -1 gpurun_out/u2_cfg1_ns2.log | cut -c1-300
+python bench.py --workload cfg1 --streams 8 --no-cpu-baseline --no-secondary > gpurun_out/u2_cfg1_ns8.log 2>/dev/null; tail -1 gpurun_out/u2_cfg1_ns8.log | cut -c1-300
+export QNNB_LIB=$PWD/quantizedneuralnetworks-keras-tensorflow_b200/libqnnb200_trace.so
+TRACE_WARPS=0,2,16 python tools/net_trace.py 100 cfg1 > gpurun_out/u2_trace_n100.log 2>&1

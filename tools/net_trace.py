@@ -29,7 +29,7 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 print("eager back-to-back: %.2f us per launch" % (e0.elapsed_time(e1) * 1e3 / 20))
-buf = torch.zeros(17 * 1024, dtype=torch.int64, device="cuda")
+buf = torch.zeros(18 * 1024, dtype=torch.int64, device="cuda")
 L.check(L.lib().qnnb_debug_set_trace(L.ptr(buf), buf.numel()))
 plan.forward(x)
 torch.cuda.synchronize()
@@ -39,7 +39,7 @@ names = {1: "entry", 2: "prologue done", 3: "griddep_wait done", 10: "MMA: layer
          20: "epi: acc ready", 21: "epi: block done", 22: "epi:   chunk loaded", 23: "epi:   chunk stored", 30: "wrk: raw image arrived", 31: "wrk: im2col built", 33: "wrk: dense(prev) done",
          34: "wrk: last dense done", 40: "teardown"}
 ev = []
-for w in range(16):
+for w in range(17):
     reg = b[w * 1024:(w + 1) * 1024]
     for i in range(int(reg[0])):
         ev.append((int(reg[3 + 2 * i]), int(reg[2 + 2 * i]) >> 32, int(reg[2 + 2 * i]) & 0xffffffff, w))
