@@ -346,7 +346,19 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     model = q.build_model(cf)
     assign_weights_from_spec(model, nodes)
     impl = {"auto": 0, "generic": 1, "tcgen05": 2}[args.kernels]
-    plan = model.plan(impl)
+    # SM share of the timed serving loop: (SMs per persistent kernel, streams).  Several independent batches in flight,
+    # each kernel on ITS share of the SMs, hide each other's pipeline fill / drain and partial last waves (measured
+    # sweep: profiles/r2_sm_share_sweep.txt).  The large configuration keeps the whole device per kernel.
+    AUTO_SHARE = {"cfg3": (37, 8), "cfg5": (74, 2), "cfg5t": (74, 2)}
+    share, auto_streams = AUTO_SHARE.get(name, (0, 0))
+    if name == "cfg3" and steps < 64:
+        share, auto_streams = 74, 4                          # a short queue: fewer batches in flight, shorter drain
+    if args.sm_share >= 0:
+        share = args.sm_share
+    if streams > 0 and args.sm_share < 0 and streams != auto_streams:
+        share = 0                                           # an explicit --streams keeps the whole-device kernels
+    plan = model.plan(impl, sm_share=share)
+    plan_alone = model.plan(impl)                           # per-kernel timing: each kernel alone on the whole device
 
     # ---- synthetic inputs: NBUF distinct resident batches, total > L2 (126 MB), rotated every step
     img_bytes = cf.dim * cf.dim * cf.channels
@@ -374,7 +386,7 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     # ---- logit gather for N > 1.  "peer" (default): rank 0 exports a ring of [world*batch, classes] buffers over CUDA
     # IPC and every rank's final dense kernel stores its block straight into it over NVLink -- no per-step collective.
     # "nccl": one all-gather per step captured inside the step's CUDA graph (one communicator per stream).
-    NS = streams if streams > 0 else (1 if name in ("cfg4", "cfg5", "cfg5t") else 4)
+    NS = streams if streams > 0 else (auto_streams if (share and auto_streams) else (1 if name in ("cfg4", "cfg5", "cfg5t") else 4))
     sts = [torch.cuda.Stream() for _ in range(NS)]
     mode, peer, groups, gflat = "none", None, None, None
     PEER_SLOTS = 8
@@ -403,10 +415,11 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     # ---- CUDA graphs: one per input buffer.  Consecutive steps are independent batches, so they are replayed
     # round-robin on NS streams (graph i always on stream i % NS, with that stream's private memory pool): the
     # tail of one batch overlaps the head of the next, as in a serving loop.
-    def step_body(i, b):
+    def step_body(i, b, pl=None):
+        pl = pl or plan
         if peer is not None:
-            return plan.forward(b, out=peer.block(i % PEER_SLOTS))
-        o = plan.forward(b)
+            return pl.forward(b, out=peer.block(i % PEER_SLOTS))
+        o = pl.forward(b)
         if mode == "nccl":
             dist.all_gather_into_tensor(gflat[i % NS], o, group=groups[i % NS])
         return o
@@ -435,13 +448,32 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
             graphs.append((g, o))
         torch.cuda.synchronize()
     nround = (ngroups // NS) * NS                      # keeps graph index -> stream mapping fixed
+    # With an SM share, the LAST batches of the queue get whole-device kernels again: once fewer batches are in flight than
+    # shares exist, a kernel confined to its share would leave the other SMs idle (what a serving loop does when its
+    # queue runs dry).  Same inputs, same arithmetic, the whole-device plan's graphs.
+    G_TOTAL = steps // SPG
+    TAIL = min(max(NS // 2, 1), G_TOTAL) if (share > 0 and graphs is not None) else 0
+    if TAIL and os.environ.get("QNNB_BENCH_TAIL"):
+        TAIL = min(int(os.environ["QNNB_BENCH_TAIL"]), G_TOTAL)
+    graphs_tail = {}
+    for gi in range(G_TOTAL - TAIL, G_TOTAL):
+        j = gi % nround
+        st = sts[j % NS]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pools[j % NS], stream=st):
+                for t in range(SPG):
+                    o = step_body(j * SPG + t, bufs[j * SPG + t], plan_alone)
+        graphs_tail[j] = (g, o)
+    torch.cuda.synchronize()
 
-    def run_group(gi):
+    def run_group(gi, tail=False):
         """SPG consecutive steps (one graph replay)."""
         j = gi % nround
         with torch.cuda.stream(sts[j % NS]):
             if graphs is not None:
-                graphs[j][0].replay()                # forward(s) (+ logit hand-over)
+                (graphs_tail if tail else graphs)[j][0].replay()   # forward(s) (+ logit hand-over)
             else:
                 step_body(j, bufs[j])
 
@@ -463,8 +495,8 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     fence_all(e0)
-    for gi in range(steps // SPG):
-        run_group(gi)
+    for gi in range(G_TOTAL):
+        run_group(gi, tail=gi >= G_TOTAL - TAIL)
     fence_all(e1)
     torch.cuda.synchronize()
     t_host1 = time.perf_counter()
@@ -490,16 +522,17 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
             gather_ok = bool(torch.equal(peer.gathered(j % PEER_SLOTS), ref))
 
     # ---- per-kernel timing (CUDA events around a graph of REPS launches, same rotating inputs) for the roofline
-    envs = [plan.run(bufs[i]) for i in range(2)]
-    work = plan_work(plan, envs[0])
-    fused = plan.fused_available(bufs[0])
-    timed_steps = list(plan.steps)
+    tplan = plan_alone
+    envs = [tplan.run(bufs[i]) for i in range(2)]
+    work = plan_work(tplan, envs[0])
+    fused = tplan.fused_available(bufs[0])
+    timed_steps = list(tplan.steps)
     if fused:
         # the whole net is ONE launch (csrc/net_fused.cu): one row -- ops of every layer; bytes = what crosses HBM, i.e. the
         # images in, the logits out and the packed kernels once
-        kern_bytes = sum(float(st.layer.kernel.size) for st in plan.steps)
+        kern_bytes = sum(float(st.layer.kernel.size) for st in tplan.steps)
         work = [("net (whole-network kernel)", float(sum(w[1] for w in work)), float(batch * (img_bytes + cf.classes * 4) + kern_bytes),
-                 ("net", cf.dim, cf.channels, tuple(st.layer.kernel.shape[-1] for st in plan.steps)))]
+                 ("net", cf.dim, cf.channels, tuple(st.layer.kernel.shape[-1] for st in tplan.steps)))]
         timed_steps = [None]
     per = np.zeros(len(timed_steps))
     REPS = 10
@@ -512,10 +545,10 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
             with torch.cuda.graph(g, stream=side):
                 for r in range(REPS):
                     if st is None:
-                        plan.forward(bufs[r % 2])
+                        tplan.forward(bufs[r % 2])
                         continue
                     env = dict(envs[r % 2])
-                    plan.run_step(st, env)
+                    tplan.run_step(st, env)
         torch.cuda.current_stream().wait_stream(side)
         g.replay()
         torch.cuda.synchronize()
@@ -556,7 +589,7 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     total_ops = float(sum(w[1] for w in work))
     res = {"workload": workload_label(name, cf, batch), "value": value, "ms_per_step": ms / steps, "steps": steps, "batch": batch,
            "parity_vs_exact_oracle": ok, "clocks": clocks, "launches_per_step": launches_per_step, "streams": NS,
-           "cuda_graphs": graphs is not None, "steps_per_graph": SPG, "nbuf": nbuf, "img_bytes": img_bytes, "classes": cf.classes, "cf": cf, "nodes": nodes,
+           "cuda_graphs": graphs is not None, "steps_per_graph": SPG, "sm_share": share, "tail_steps": TAIL * SPG, "nbuf": nbuf, "img_bytes": img_bytes, "classes": cf.classes, "cf": cf, "nodes": nodes,
            "roofline": roof, "gather": mode, "gather_verified": gather_ok,
            "int8_tops_achieved": total_ops / (ms / steps * 1e-3) / 1e12, "int8_frac_of_burst_peak": total_ops / (ms / steps * 1e-3) / 1e12 / i8_burst}
 
@@ -662,7 +695,10 @@ def run_ours(args):
                 "config": {"workload": m["workload"], "global_batch": batch * world, "parallelism": par,
                            "l2_policy": "inputs larger than L2: %d distinct resident batches (%.0f MB) rotated every step" % (
                                m["nbuf"], m["nbuf"] * batch * m["img_bytes"] / 1e6),
-                           "cuda_graphs": m["cuda_graphs"], "steps_per_graph": m["steps_per_graph"], "streams": m["streams"], "kernels": args.kernels,
+                           "cuda_graphs": m["cuda_graphs"], "steps_per_graph": m["steps_per_graph"], "streams": m["streams"],
+                           "sm_share": ("%d SMs per kernel: %d independent batches in flight, their kernels side by side (the last %d steps of the queue "
+                                        "get whole-device kernels); roofline.per_kernel_ms times each kernel alone on the whole device"
+                                        % (m["sm_share"], m["streams"], m["tail_steps"])) if m["sm_share"] else "whole device per kernel", "kernels": args.kernels,
                            "parity_vs_exact_oracle": m["parity_vs_exact_oracle"]},
                 "clocks": m["clocks"], "gpu_launches": m["launches_per_step"] * args.steps,
                 "e2e": m["e2e"], "roofline": m["roofline"],
@@ -697,6 +733,7 @@ def main():
     ap.add_argument("--kernels", default="auto", choices=["auto", "generic", "tcgen05"])
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--streams", type=int, default=0, help="0 = auto: 4 for short steps, 1 for the large config")
+    ap.add_argument("--sm-share", type=int, default=-1, help="SMs per persistent kernel in the timed loop (-1 = per-workload default, 0 = all)")
     ap.add_argument("--ref-sample", type=int, default=256)
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="world > 1: logits stored into rank 0's peer-mapped buffer by the dense kernel (NVLink), or one NCCL all-gather per step")

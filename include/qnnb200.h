@@ -101,6 +101,9 @@ typedef struct qnnb_conv_desc {
   int32_t impl;             /* QNNB_IMPL_* */
   qnnb_epilogue epi;
   int32_t w_f32;            /* 1: `w` is a QNNB_WFMT_F32 kernel (fp32 values, 'float' networks); needs in_kind F32.  0: levels */
+  int32_t max_ctas;         /* SM share: 0 = the persistent kernels take one CTA per SM of the device; k > 0 = at most k CTAs, so
+                               that the kernels of independent batches running on other streams sit NEXT to this one (each on
+                               its own SMs) and fill each other's pipeline fill / drain and last partial wave */
 } qnnb_conv_desc;
 
 /* Dense layer  y[n][u] = epilogue( sum_f x[n][f] * w[u][f] ), optional softmax. */
@@ -113,6 +116,7 @@ typedef struct qnnb_dense_desc {
                                positions -- AveragePooling2D(8) + Flatten of models/resnet.py:134-135 folded in; acc_scale
                                carries the 1/P */
   int32_t w_f32;            /* 1: `w` is a QNNB_WFMT_F32 kernel; needs in_kind F32 */
+  int32_t max_ctas;         /* SM share, as in qnnb_conv_desc */
 } qnnb_dense_desc;
 
 int         qnnb_version(void);
@@ -213,6 +217,7 @@ typedef struct qnnb_vgg_desc {
   int32_t       units;
   const void*   dense_w;
   qnnb_epilogue dense_epi;  /* act NONE */
+  int32_t       max_ctas;   /* SM share, as in qnnb_conv_desc (0 = min(n, SMs) CTAs, one image each at a time) */
 } qnnb_vgg_desc;
 
 /* 1 when qnnb_vgg_forward covers this net, else 0 (the host then runs the per-layer plan) */

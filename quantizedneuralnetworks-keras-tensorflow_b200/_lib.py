@@ -48,6 +48,7 @@ class ConvDesc(C.Structure):
         ("impl", C.c_int32),
         ("epi", Epilogue),
         ("w_f32", C.c_int32),
+        ("max_ctas", C.c_int32),
     ]
 
 
@@ -59,6 +60,7 @@ class DenseDesc(C.Structure):
         ("epi", Epilogue),
         ("avg_positions", C.c_int32),
         ("w_f32", C.c_int32),
+        ("max_ctas", C.c_int32),
     ]
 
 
@@ -77,6 +79,7 @@ class VggDesc(C.Structure):
         ("units", C.c_int32),
         ("dense_w", C.c_void_p),
         ("dense_epi", Epilogue),
+        ("max_ctas", C.c_int32),
     ]
 
 

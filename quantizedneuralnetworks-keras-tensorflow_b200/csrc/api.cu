@@ -41,6 +41,7 @@ static int validate_conv(const qnnb_conv_desc& d) {
   QNNB_CHECK_ARG(d.in_kind == QNNB_KIND_U8 || d.in_kind == QNNB_KIND_I8 || d.in_kind == QNNB_KIND_B1 || d.in_kind == QNNB_KIND_F32,
                  "conv2d: bad in_kind %d", d.in_kind);
   QNNB_CHECK_ARG(d.w_f32 == 0 || (d.w_f32 == 1 && d.in_kind == QNNB_KIND_F32), "conv2d: an fp32 kernel (w_f32) needs fp32 activations");
+  QNNB_CHECK_ARG(d.max_ctas >= 0, "conv2d: max_ctas=%d must be >= 0", d.max_ctas);
   int rc = validate_epilogue(d.epi, true, true);
   if (rc) return rc;
   if (d.epi.pool) {
@@ -153,6 +154,7 @@ int qnnb_dense(const qnnb_dense_desc* d, const void* x, const void* w, float* y,
   if (rc) return rc;
   QNNB_CHECK_ARG(d->epi.act == QNNB_ACT_NONE, "dense: fused activation not supported (act=%d)", d->epi.act);
   QNNB_CHECK_ARG(d->w_f32 == 0 || (d->w_f32 == 1 && d->in_kind == QNNB_KIND_F32), "dense: an fp32 kernel (w_f32) needs fp32 input");
+  QNNB_CHECK_ARG(d->max_ctas >= 0, "dense: max_ctas=%d must be >= 0", d->max_ctas);
   QNNB_CHECK_ARG(d->avg_positions >= 0 && (d->avg_positions <= 1 || d->in_kind == QNNB_KIND_F32),
                  "dense: avg_positions=%d needs fp32 input", d->avg_positions);
   if (d->n == 0) return QNNB_OK;
@@ -169,6 +171,7 @@ static int validate_vgg(const qnnb_vgg_desc* d, const char* who) {
   QNNB_CHECK_ARG(d, "%s: null descriptor", who);
   QNNB_CHECK_ARG(d->n >= 0, "%s: bad batch size %d", who, d->n);
   QNNB_CHECK_ARG(d->nconv >= 1 && d->nconv <= QNNB_NET_MAX_CONVS, "%s: nconv=%d outside 1..%d", who, d->nconv, QNNB_NET_MAX_CONVS);
+  QNNB_CHECK_ARG(d->max_ctas >= 0, "%s: max_ctas=%d must be >= 0", who, d->max_ctas);
   for (int l = 0; l < d->nconv; ++l) {
     int rc = validate_epilogue(d->conv[l].epi, true, false);
     if (rc) return rc;

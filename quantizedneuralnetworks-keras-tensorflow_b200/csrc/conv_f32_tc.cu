@@ -631,7 +631,7 @@ int launch_conv_f32_tc(const qnnb_conv_desc& d, const void* x, const void* w, vo
   p.wpk = (const int8_t*)w;
   p.y = (float*)y;
   p.epi = make_epi(d.epi);
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const int grid = p.num_tiles < grid_sms(d.max_ctas) ? p.num_tiles : grid_sms(d.max_ctas);
   if (TH == 16) return launch_th<16>(mx, mr, my, p, grid, st);
   return launch_th<8>(mx, mr, my, p, grid, st);
 }

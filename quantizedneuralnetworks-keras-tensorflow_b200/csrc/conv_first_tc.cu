@@ -674,7 +674,7 @@ int launch_conv_first_tc(const qnnb_conv_desc& d, const void* x, const void* w, 
   { const char* ev = getenv("QNNB_K5_EXP"); p.exp = ev ? atoi(ev) : 0; }
   p.epi = make_epi(d.epi);
   p.qlo = -p.epi.qm; p.qhi = p.epi.qm - 1.f;
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const int grid = p.num_tiles < grid_sms(d.max_ctas) ? p.num_tiles : grid_sms(d.max_ctas);
   CUtensorMap my;
   memset(&my, 0, sizeof(my));
   if (!f32) {

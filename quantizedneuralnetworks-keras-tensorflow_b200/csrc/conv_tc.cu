@@ -930,7 +930,7 @@ int launch_conv_tc_v2(const qnnb_conv_desc& d, const void* x, const void* w, voi
   p.out_pitch = TILE_M;
   p.y = y;
   p.epi = make_epi(d.epi);
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const int grid = p.num_tiles < grid_sms(d.max_ctas) ? p.num_tiles : grid_sms(d.max_ctas);
   // Cin = 64: all nine taps (72 KB) fit the nine-stage weight ring; if every tile of a CTA uses the same channel tile they
   // are loaded once and stay (no per-tap barrier traffic afterwards)
   p.resident = (KC == 64 && p.kchunks == 1 && (p.m_tiles == 1 || grid % p.m_tiles == 0) && getenv("QNNB_NO_RESIDENT") == nullptr) ? 1 : 0;
@@ -1031,7 +1031,7 @@ int launch_conv_tc(const qnnb_conv_desc& d, const void* x, const void* w, void* 
   p.y = y;
   p.epi = make_epi(d.epi);
 
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const int grid = p.num_tiles < grid_sms(d.max_ctas) ? p.num_tiles : grid_sms(d.max_ctas);
   if (KC == 128) return launch_kc<128, 4>(mw, mx, my, p, grid, g.tw, pool, f32, st);
   return launch_kc<64, 6>(mw, mx, my, p, grid, g.tw, pool, f32, st);
 #endif

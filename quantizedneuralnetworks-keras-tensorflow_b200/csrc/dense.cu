@@ -9,6 +9,7 @@
 // HBM-bound (reads fin bytes per image, writes 40): x is read once, coalesced, 128 B per warp
 // per step; the packed kernel (<= 40 KB) stays in L1/L2.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace qnnb {
 
@@ -283,13 +284,14 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
   if (blocks < 1) blocks = 1;
   if (d.avg_positions > 1) {
     QNNB_CHECK_ARG(d.in_kind == QNNB_KIND_F32 && d.fin <= 256, "dense: avg_positions needs fp32 input with fin <= 256 (got kind %d, fin %d)", d.in_kind, d.fin);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > tcx::grid_sms(d.max_ctas) * 8) blocks = tcx::grid_sms(d.max_ctas) * 8;
     QNNB_CUDA(launch_pdl(dense_avgpool_f32_kernel, dim3(blocks), dim3(256), (size_t)0, st, p, (int)d.avg_positions));
     return QNNB_OK;
   }
   const size_t wbytes = (size_t)d.units * p.kwords * 4;
   if (d.in_kind != QNNB_KIND_F32 && d.units <= UG && (p.kwords & 3) == 0 && wbytes <= 160 * 1024) {
-    int fb = blocks > 148 * 2 ? 148 * 2 : blocks;
+    const int cap = tcx::grid_sms(d.max_ctas) * 2;
+    int fb = blocks > cap ? cap : blocks;
     if (d.in_kind == QNNB_KIND_I8) {
       QNNB_CUDA(cudaFuncSetAttribute(dense_smem_kernel<QNNB_KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
       QNNB_CUDA(launch_pdl(dense_smem_kernel<QNNB_KIND_I8>, dim3(fb), dim3(256), wbytes, st, p));
@@ -300,7 +302,7 @@ int launch_dense(const qnnb_dense_desc& d, const void* x, const void* w, float* 
     QNNB_CUDA(cudaGetLastError());
     return QNNB_OK;
   }
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > tcx::grid_sms(d.max_ctas) * 8) blocks = tcx::grid_sms(d.max_ctas) * 8;
   switch (d.in_kind) {
     case QNNB_KIND_I8: dense_kernel<QNNB_KIND_I8><<<blocks, 256, 0, st>>>(p); break;
     case QNNB_KIND_B1: dense_kernel<QNNB_KIND_B1><<<blocks, 256, 0, st>>>(p); break;

@@ -814,7 +814,7 @@ int launch_vgg_fused(const qnnb_vgg_desc& d, const void* blob, const void* x, fl
   p.tr = get_trace_buffer();
   static SmemConfigured once;
   QNNB_CUDA(once.ensure(vgg_fused_kernel, smem));
-  const int grid = d.n < sm_count() ? d.n : sm_count();
+  const int grid = d.n < grid_sms(d.max_ctas) ? d.n : grid_sms(d.max_ctas);
   QNNB_CUDA(launch_pdl(vgg_fused_kernel, dim3(grid), dim3(NF_THREADS), (size_t)smem, st, p));
   return QNNB_OK;
 }

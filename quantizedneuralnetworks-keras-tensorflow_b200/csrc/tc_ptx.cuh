@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define QNNB_STR2(x) #x
 #define QNNB_STR(x) QNNB_STR2(x)
@@ -305,6 +306,13 @@ static inline int sm_count() {
   if (dev < 0 || dev >= 64) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }
   if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
   return sms[dev];
+}
+
+// CTAs of a persistent grid: one per SM, or `max_ctas` of them when the caller shares the device between the kernels of
+// several independent batches (descriptor field max_ctas; 0 = all SMs)
+static inline int grid_sms(int max_ctas) {
+  const int s = sm_count();
+  return (max_ctas > 0 && max_ctas < s) ? max_ctas : s;
 }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of the (function, device) pair: remember per

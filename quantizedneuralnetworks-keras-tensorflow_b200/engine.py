@@ -417,11 +417,13 @@ class _ModelBase:
         self._invalidate()
 
     # ---- inference
-    def plan(self, impl=0):
+    def plan(self, impl=0, sm_share=0):
+        """The fused launch plan for kernel selection ``impl`` (0 = automatic); ``sm_share`` = SMs per persistent kernel
+        (0 = all; see plan.Plan)."""
         from .plan import Plan
-        key = int(impl)
+        key = (int(impl), int(sm_share)) if sm_share else int(impl)
         if key not in self._plans:
-            self._plans[key] = Plan(self, impl=key)
+            self._plans[key] = Plan(self, impl=int(impl), sm_share=int(sm_share))
         return self._plans[key]
 
     def predict(self, x, batch_size=None, verbose=0, impl=0, return_logits=False):

@@ -113,7 +113,7 @@ def acc_scale(x_scale: float, w_scale: float) -> np.float32:
 
 
 # --------------------------------------------------------------------------- conv / dense
-def _conv_desc(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, impl) -> L.ConvDesc:
+def _conv_desc(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, impl, max_ctas=0) -> L.ConvDesc:
     n, h, w, cin = (int(v) for v in x.shape)
     d = L.ConvDesc()
     d.n, d.h, d.w, d.cin = n, h, w, cin
@@ -122,6 +122,7 @@ def _conv_desc(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, impl) -> L.Con
     d.impl = int(impl)
     d.epi = epi
     d.w_f32 = 0
+    d.max_ctas = int(max_ctas)
     return d
 
 
@@ -135,10 +136,11 @@ def conv2d_on_tensor_cores(x: QTensor, kh, kw, cout, stride, epi: L.Epilogue, im
 
 
 def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epilogue, impl=L.IMPL_AUTO,
-           out: torch.Tensor | None = None) -> QTensor:
-    """``w_packed`` of dtype float32 is a QNNB_WFMT_F32 kernel ('float' networks; fp32 activations only)."""
+           out: torch.Tensor | None = None, max_ctas=0) -> QTensor:
+    """``w_packed`` of dtype float32 is a QNNB_WFMT_F32 kernel ('float' networks; fp32 activations only).  ``max_ctas``:
+    SM share of the persistent kernels (0 = the whole device; see qnnb_conv_desc.max_ctas)."""
     n, h, w, cin = (int(v) for v in x.shape)
-    d = _conv_desc(x, kh, kw, cout, stride, epi, impl)
+    d = _conv_desc(x, kh, kw, cout, stride, epi, impl, max_ctas)
     d.w_f32 = 1 if w_packed.dtype == torch.float32 else 0
     oh, ow = C.c_int32(), C.c_int32()
     L.check(L.lib().qnnb_conv2d_out_shape(C.byref(d), C.byref(oh), C.byref(ow)))
@@ -161,7 +163,7 @@ def conv2d(x: QTensor, w_packed: torch.Tensor, kh, kw, cout, stride, epi: L.Epil
 
 
 def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=False, want_logits=False,
-          out: torch.Tensor | None = None, logits: torch.Tensor | None = None, avg_positions=0):
+          out: torch.Tensor | None = None, logits: torch.Tensor | None = None, avg_positions=0, max_ctas=0):
     """``avg_positions`` = P > 1 (fp32 input): ``x`` is [n, P*fin] laid out [n][P][fin]; the layer input is the sum over
     the P positions (global average pooling folded in, the 1/P is part of ``epi.acc_scale``)."""
     n = int(x.data.shape[0])
@@ -177,6 +179,7 @@ def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=Fa
     d.softmax = 1 if softmax else 0
     d.epi = epi
     d.w_f32 = 1 if w_packed.dtype == torch.float32 else 0
+    d.max_ctas = int(max_ctas)
     dev = x.data.device
     if out is None:
         out = torch.empty((n, units), dtype=torch.float32, device=dev)
@@ -190,7 +193,7 @@ def dense(x: QTensor, w_packed: torch.Tensor, units, epi: L.Epilogue, softmax=Fa
 
 
 # --------------------------------------------------------------------------- whole-network launch
-def vgg_desc(n, h, w, cin, convs, units, dense_w, dense_epi) -> L.VggDesc:
+def vgg_desc(n, h, w, cin, convs, units, dense_w, dense_epi, max_ctas=0) -> L.VggDesc:
     """``convs``: list of (cout, pool, packed kernel, Epilogue) -- see ``qnnb_vgg_desc`` in include/qnnb200.h."""
     d = L.VggDesc()
     d.n, d.h, d.w, d.cin = int(n), int(h), int(w), int(cin)
@@ -204,6 +207,7 @@ def vgg_desc(n, h, w, cin, convs, units, dense_w, dense_epi) -> L.VggDesc:
     d.units = int(units)
     d.dense_w = L.ptr(dense_w)
     d.dense_epi = dense_epi
+    d.max_ctas = int(max_ctas)
     d._refs = (convs, dense_w, dense_epi)
     return d
 

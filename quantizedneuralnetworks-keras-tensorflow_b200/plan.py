@@ -66,12 +66,17 @@ class _Handle:
 
 
 class Plan:
-    def __init__(self, model, impl=L.IMPL_AUTO):
+    def __init__(self, model, impl=L.IMPL_AUTO, sm_share=0):
+        """``sm_share``: CTAs (= SMs) each persistent kernel of this plan may take; 0 = the whole device.  A serving loop
+        that keeps several independent batches in flight on different streams gives every plan a share (e.g. 37 of
+        148 SMs with eight streams): kernels of different batches then run side by side and hide each other's pipeline
+        fill / drain and partial last waves -- per-batch latency rises, throughput rises too."""
         # weak: the model owns its plans (model._plans); a strong back-reference would make every dead model -- with
         # the CUDA graphs and pool memory of its plans -- wait for the cyclic collector, which may then run in the
         # middle of somebody else's stream capture
         self._model_ref = weakref.ref(model)
         self.impl = int(impl)
+        self.sm_share = int(sm_share)
         ins, outs = model._graph()
         self.order = E.topo_order(outs)
         self.index = {id(t): i for i, t in enumerate(self.order)}
@@ -266,7 +271,7 @@ class Plan:
             if K.conv2d_on_tensor_cores(x, lay.kernel_size[0], lay.kernel_size[1], lay.filters, lay.strides[0], epi8, self.impl):
                 epi = epi8
         env[st.out] = K.conv2d(x, lay.packed_kernel(dev, wfmt), lay.kernel_size[0], lay.kernel_size[1], lay.filters,
-                               lay.strides[0], epi, impl=self.impl)
+                               lay.strides[0], epi, impl=self.impl, max_ctas=self.sm_share)
         self.launches += 1
 
     def _resolve_dense_input(self, idx, env):
@@ -339,7 +344,7 @@ class Plan:
         # network output directly when this layer produces it
         dst = env.get("out_buffer") if st.out == self.output_idx else None
         out, logits = K.dense(xin, wp, lay.units, epi, softmax=st.softmax, want_logits=st.softmax, avg_positions=avg_positions,
-                              out=dst)
+                              out=dst, max_ctas=self.sm_share)
         if dst is not None:
             env["out_buffer_used"] = True
         env[st.out] = K.QTensor("f32", out, 1.0, lay.units)
@@ -422,7 +427,8 @@ class Plan:
         if dn.bn is not None:
             inv, shift = self._bn_dev(dn, dn.bn, dev)
         depi = K.make_epilogue(K.acc_scale(scale_in, wscale), bias=lay.bias_tensor(dev), bn_inv=inv, bn_shift=shift)
-        d = K.vgg_desc(n, int(x.shape[1]), int(x.shape[2]), cin, rows, lay.units, lay.packed_kernel(dev, L.WFMT_I8), depi)
+        d = K.vgg_desc(n, int(x.shape[1]), int(x.shape[2]), cin, rows, lay.units, lay.packed_kernel(dev, L.WFMT_I8), depi,
+                       max_ctas=self.sm_share)
         return d if K.vgg_forward_supported(d) else None
 
     def fused_available(self, x) -> bool:

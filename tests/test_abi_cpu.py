@@ -61,6 +61,8 @@ int main(void) {
          offsetof(qnnb_epilogue, pool), offsetof(qnnb_dense_desc, avg_positions));
   printf("%zu %zu %zu %zu %zu %zu %d\n", sizeof(qnnb_net_conv), sizeof(qnnb_vgg_desc), offsetof(qnnb_net_conv, epi),
          offsetof(qnnb_vgg_desc, conv), offsetof(qnnb_vgg_desc, dense_w), offsetof(qnnb_vgg_desc, dense_epi), QNNB_NET_MAX_CONVS);
+  printf("%zu %zu %zu %zu %zu\n", offsetof(qnnb_conv_desc, w_f32), offsetof(qnnb_conv_desc, max_ctas), offsetof(qnnb_dense_desc, w_f32),
+         offsetof(qnnb_dense_desc, max_ctas), offsetof(qnnb_vgg_desc, max_ctas));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -70,7 +72,9 @@ int main(void) {
     want = [C.sizeof(L.Epilogue), C.sizeof(L.ConvDesc), C.sizeof(L.DenseDesc), L.ConvDesc.epi.offset,
             L.DenseDesc.epi.offset, L.Epilogue.residual.offset, L.Epilogue.pool.offset, L.DenseDesc.avg_positions.offset,
             C.sizeof(L.NetConv), C.sizeof(L.VggDesc), L.NetConv.epi.offset, L.VggDesc.conv.offset, L.VggDesc.dense_w.offset,
-            L.VggDesc.dense_epi.offset, L.NET_MAX_CONVS]
+            L.VggDesc.dense_epi.offset, L.NET_MAX_CONVS,
+            L.ConvDesc.w_f32.offset, L.ConvDesc.max_ctas.offset, L.DenseDesc.w_f32.offset, L.DenseDesc.max_ctas.offset,
+            L.VggDesc.max_ctas.offset]
     assert got == want
 
 
