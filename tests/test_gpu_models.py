@@ -425,3 +425,31 @@ def test_full_size_batches_properties(name, n, chunk):
     else:
         assert rel_err(full[idx], want) <= 1e-4
         assert np.array_equal(full[idx].argmax(1), want.argmax(1))
+
+
+@pytest.mark.parametrize("name,n", [("cfg3", 300), ("cfg2", 64), ("cfg1", 100), ("cfg5", 8)])
+def test_sm_share_gives_identical_results(name, n):
+    """Plan(sm_share=k) sizes every persistent grid for k SMs (qnnb_*_desc.max_ctas) so that kernels of independent
+    batches can run side by side; the tile -> CTA assignment changes, the arithmetic must not: bit-identical outputs
+    for every share, also when batches on different streams really do overlap."""
+    cf, model, nodes = build(CONFIGS[name], bn="spread")
+    x = torch.from_numpy(images(cf, n)).cuda()
+    want = model.plan().forward(x).clone()
+    for share in (1, 37, 74, 1000):
+        got = model.plan(sm_share=share).forward(x)
+        assert torch.equal(got, want), "sm_share=%d changes the result" % share
+    # four batches in flight on four streams, 37 SMs per kernel
+    plan = model.plan(sm_share=37)
+    xs = [torch.from_numpy(images(cf, n, seed=100 + i)).cuda() for i in range(4)]
+    refs = [model.plan().forward(xi).clone() for xi in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    outs = []
+    for rep in range(3):
+        for xi, st in zip(xs, streams):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                outs.append(plan.forward(xi))
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, refs[i % 4])
