@@ -349,10 +349,13 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     # SM share of the timed serving loop: (SMs per persistent kernel, streams).  Several independent batches in flight,
     # each kernel on ITS share of the SMs, hide each other's pipeline fill / drain and partial last waves (measured
     # sweep: profiles/r2_sm_share_sweep.txt).  The large configuration keeps the whole device per kernel.
-    AUTO_SHARE = {"cfg3": (37, 8), "cfg5": (74, 2), "cfg5t": (74, 2)}
+    AUTO_SHARE = {"cfg3": (37, 8), "cfg2": (37, 8), "cfg5": (74, 2), "cfg5t": (74, 2)}
     share, auto_streams = AUTO_SHARE.get(name, (0, 0))
-    if name == "cfg3" and steps < 64:
-        share, auto_streams = 74, 4                          # a short queue: fewer batches in flight, shorter drain
+    if steps < 64:                                           # a short queue: fewer batches in flight, shorter drain
+        if name == "cfg3":
+            share, auto_streams = 74, 4
+        elif name == "cfg2":
+            share, auto_streams = 0, 0
     if args.sm_share >= 0:
         share = args.sm_share
     if streams > 0 and args.sm_share < 0 and streams != auto_streams:
@@ -424,12 +427,12 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
             dist.all_gather_into_tensor(gflat[i % NS], o, group=groups[i % NS])
         return o
 
-    # A step of the tiny configuration (cfg1: 100 images, one 12 us launch) is shorter than the host's cost of replaying
-    # a graph, so SPG consecutive steps (distinct input batches) are captured per graph; SPG divides `steps`, so the
-    # timed region is still exactly `steps` steps.
+    # A step of the small configurations (cfg1: 100 images, one 12 us launch; cfg2: 256 images, 13-21 us) is about as
+    # long as the host's cost of replaying a graph, so SPG consecutive steps (distinct input batches) are captured per
+    # graph; SPG divides `steps`, so the timed region is still exactly `steps` steps.
     SPG = 1
-    if args.graphs and batch * img_bytes <= 262144:
-        SPG = max(d for d in range(1, 9) if steps % d == 0)
+    if args.graphs and batch * img_bytes <= int(os.environ.get("QNNB_BENCH_SPG_BYTES", "1000000")):
+        SPG = max(d for d in range(1, 9) if steps % d == 0 and nbuf // d >= NS)
     ngroups = nbuf // SPG
     graphs = None
     if args.graphs:
@@ -668,9 +671,10 @@ def run_ours(args):
     # 60 % tensor-core target is stated on (BASELINE.json configs[3]), the XNOR config and the ResNet config
     secondary = {}
     if world == 1 and args.workload == "cfg3" and not args.no_secondary:
-        for nm, st in (("cfg4", 20), ("cfg2", 100), ("cfg5", 20)):
+        for nm, st in (("cfg4", 20), ("cfg2", 200), ("cfg5", 20)):
             try:
-                r = measure(args, nm, ctx, min(st, max(args.steps, 3)), 3, full=False)
+                # own step counts (a secondary run is 2-100 ms of GPU time); tiny --steps (smoke runs) shrink them too
+                r = measure(args, nm, ctx, st if args.steps >= 10 else min(st, max(args.steps, 3)), 3, full=False)
                 ro = r["roofline"]
                 secondary[nm] = {"workload": r["workload"], "value": r["value"], "unit": "images/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
                                  "parity_vs_exact_oracle": r["parity_vs_exact_oracle"], "clocks": r["clocks"],

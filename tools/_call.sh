@@ -1,6 +1,5 @@
-for n in 8 4 2; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_${n}gpu.json 2> gpurun_out/r2p_cfg3_${n}gpu.err
-  tail -1 gpurun_out/r2p_final_cfg3_${n}gpu.json | cut -c1-230
-done
-python bench.py --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_1gpu_same_box.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg3_1gpu_same_box.json | cut -c1-230
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 200 --warmup 10 --no-secondary --no-cpu-baseline > gpurun_out/r2p_final_cfg3_8gpu_s200.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg3_8gpu_s200.json | cut -c1-230
+python bench.py --steps 20 --warmup 5 > gpurun_out/v3_default.log 2>gpurun_out/v3_default.err; tail -1 gpurun_out/v3_default.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['e2e']['value'], d['roofline']['step_frac']); print({k:(round(v['value']), v['steps'], v['roofline']['frac'], v['roofline']['step_frac']) for k,v in d['secondary'].items()})"
+tail -3 gpurun_out/v3_default.err
+python bench.py --workload cfg2 --no-cpu-baseline --no-secondary > gpurun_out/v3_cfg2.log 2>/dev/null; tail -1 gpurun_out/v3_cfg2.log | cut -c1-250
+python bench.py --workload cfg2 --batch 1024 --no-cpu-baseline --no-secondary > gpurun_out/v3_cfg2_b1024.log 2>/dev/null; tail -1 gpurun_out/v3_cfg2_b1024.log | cut -c1-250
