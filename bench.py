@@ -427,11 +427,12 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
             dist.all_gather_into_tensor(gflat[i % NS], o, group=groups[i % NS])
         return o
 
-    # A step of the small configurations (cfg1: 100 images, one 12 us launch; cfg2: 256 images, 13-21 us) is about as
-    # long as the host's cost of replaying a graph, so SPG consecutive steps (distinct input batches) are captured per
-    # graph; SPG divides `steps`, so the timed region is still exactly `steps` steps.
+    # SPG consecutive steps (distinct input batches) are captured per graph, so the timed region is a handful of graph
+    # replays issued up front: a step of the small configurations (cfg1: one 12 us launch; cfg2: 13-21 us) is about as long
+    # as the host's cost of replaying a graph, and even for the 40 us steps a single host hiccup between replays would
+    # show up in a 20-step window.  SPG divides `steps`, so the timed region is still exactly `steps` steps.
     SPG = 1
-    if args.graphs and batch * img_bytes <= int(os.environ.get("QNNB_BENCH_SPG_BYTES", "1000000")):
+    if args.graphs and len(plan.steps) <= 6 and batch * img_bytes <= 4000000:      # short steps only: coarse groups lengthen the drain
         SPG = max(d for d in range(1, 9) if steps % d == 0 and nbuf // d >= NS)
     ngroups = nbuf // SPG
     graphs = None
@@ -455,7 +456,9 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     # shares exist, a kernel confined to its share would leave the other SMs idle (what a serving loop does when its
     # queue runs dry).  Same inputs, same arithmetic, the whole-device plan's graphs.
     G_TOTAL = steps // SPG
-    TAIL = min(max(NS // 2, 1), G_TOTAL) if (share > 0 and graphs is not None) else 0
+    TAIL = 0
+    if share > 0 and graphs is not None and G_TOTAL > NS:
+        TAIL = 1 if SPG > 1 else max(NS // 2, 1)
     if TAIL and os.environ.get("QNNB_BENCH_TAIL"):
         TAIL = min(int(os.environ["QNNB_BENCH_TAIL"]), G_TOTAL)
     graphs_tail = {}
@@ -489,8 +492,10 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
         for st in sts:
             st.wait_stream(cur)
 
-    for gi in range(-(-max(warmup, 3) // SPG)):
-        run_group(gi)
+    # warm-up: at least `warmup` steps, and every graph the timed region will replay once (the first launch of a CUDA
+    # graph uploads it to the device: tens of microseconds that are not part of a step)
+    for gi in range(max(-(-max(warmup, 3) // SPG), min(G_TOTAL, nround))):
+        run_group(gi, tail=gi >= G_TOTAL - TAIL)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
