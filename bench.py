@@ -349,12 +349,12 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     # SM share of the timed serving loop: (SMs per persistent kernel, streams).  Several independent batches in flight,
     # each kernel on ITS share of the SMs, hide each other's pipeline fill / drain and partial last waves (measured
     # sweep: profiles/r2_sm_share_sweep.txt).  The large configuration keeps the whole device per kernel.
-    AUTO_SHARE = {"cfg3": (37, 8), "cfg2": (37, 8), "cfg5": (74, 2), "cfg5t": (74, 2)}
+    AUTO_SHARE = {"cfg3": (37, 8), "cfg2": (37, 8), "cfg1": (37, 8), "cfg5": (74, 2), "cfg5t": (74, 2)}
     share, auto_streams = AUTO_SHARE.get(name, (0, 0))
     if steps < 64:                                           # a short queue: fewer batches in flight, shorter drain
         if name == "cfg3":
             share, auto_streams = 74, 4
-        elif name == "cfg2":
+        elif name in ("cfg2", "cfg1"):
             share, auto_streams = 0, 0
     if args.sm_share >= 0:
         share = args.sm_share
@@ -459,8 +459,6 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
     TAIL = 0
     if share > 0 and graphs is not None and G_TOTAL > NS:
         TAIL = 1 if SPG > 1 else max(NS // 2, 1)
-    if TAIL and os.environ.get("QNNB_BENCH_TAIL"):
-        TAIL = min(int(os.environ["QNNB_BENCH_TAIL"]), G_TOTAL)
     graphs_tail = {}
     for gi in range(G_TOTAL - TAIL, G_TOTAL):
         j = gi % nround
