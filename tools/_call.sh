@@ -1,2 +1,4 @@
-python bench.py --workload cfg1 --no-secondary > gpurun_out/r2p_final_cfg1.json 2>/dev/null; tail -1 gpurun_out/r2p_final_cfg1.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step']*1e3,2), d['config']['sm_share'][:20], d['config']['streams'], d['config']['steps_per_graph'], round(d['e2e']['value']))"
-python bench.py --workload cfg1 --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/v7.json 2>/dev/null; tail -1 gpurun_out/v7.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('20 steps', round(d['value']), round(d['ms_per_step']*1e3,2), d['config']['streams'], d['config']['steps_per_graph'])"
+export QNNB_LIB=$PWD/quantizedneuralnetworks-keras-tensorflow_b200/libqnnb200_trace.so
+export TRACE_WARPS=0,1,5,9,13,17 TRACE_TILES=7
+python tools/k5_trace.py 1036 64 1 4 > gpurun_out/w2_trace.log 2>&1
+for e in 0 1 9 15 13; do QNNB_K5_EXP=$e python tools/k5_probe.py 2072 64 1 4 2>&1 | tail -1; done
