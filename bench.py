@@ -600,7 +600,7 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
            "int8_tops_achieved": total_ops / (ms / steps * 1e-3) / 1e12, "int8_frac_of_burst_peak": total_ops / (ms / steps * 1e-3) / 1e12 / i8_burst}
 
     # ---- end to end through the public API: pinned host batch -> H2D -> fused plan (CUDA graph) -> D2H logits,
-    # every step; steps are software-pipelined three deep (model.predict_async), as a serving loop would.
+    # every step; steps are software-pipelined PIPELINE_DEPTH (four) deep (model.predict_async), as a serving loop would.
     if full:
         torch.cuda.synchronize()
         for i in range(3):
@@ -611,12 +611,13 @@ def measure(args, name, ctx, steps, warmup, streams=0, full=True):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        depth = model.plan(impl).PIPELINE_DEPTH
         t0 = time.perf_counter()
         pending = []
         checksum = 0.0
         for i in range(steps):
             pending.append(model.predict_async(host[i % len(host)], impl=impl))
-            if len(pending) >= 3:
+            if len(pending) >= depth:
                 checksum += float(pending.pop(0).result()[0, 0])
         for h in pending:
             checksum += float(h.result()[0, 0])

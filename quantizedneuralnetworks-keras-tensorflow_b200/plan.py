@@ -479,7 +479,9 @@ class Plan:
     # A host batch goes through one of PIPELINE_DEPTH slots: its own stream, a static device input, the whole
     # fused plan captured once as a CUDA graph, and a pinned result buffer.  H2D copy, graph replay and D2H
     # copy are enqueued back to back on the slot's stream, so consecutive batches overlap copy and compute.
-    PIPELINE_DEPTH = 3
+    # Four slots: with three, the host has ~40 us per step to re-issue a slot before the copy engine runs dry (a 3 MB batch is
+    # 62 us of PCIe time); four keep the link busy through ordinary host jitter (13.9 -> 14.8 M img/s end to end on cfg3).
+    PIPELINE_DEPTH = 4
 
     def _capture(self, x_dev, st):
         """Capture one forward over the static input ``x_dev`` on stream ``st``.  Returns (graph | None, output).

@@ -298,7 +298,7 @@ def test_predict_async_handles_survive_slot_recycling():
     """More outstanding handles than pipeline slots, read late and out of order: every handle returns ITS batch."""
     cf, model, nodes = build(CONFIGS["cfg3"], bn="spread")
     batches = [images(cf, 8, seed=100 + i) for i in range(8)]
-    handles = [model.predict_async(b) for b in batches]          # PIPELINE_DEPTH = 3 slots, 8 handles
+    handles = [model.predict_async(b) for b in batches]          # PIPELINE_DEPTH slots, 8 handles
     for i in (7, 0, 3, 5, 1, 2, 6, 4):
         assert np.array_equal(handles[i].result().numpy(), exact.forward(nodes, batches[i])), "handle %d" % i
 
